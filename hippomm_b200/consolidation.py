@@ -1,0 +1,74 @@
+"""Memory consolidation: drop-in for HippocampalMemory._select_key_frames (hm:944-967)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cuda, _lib
+
+# similarity bands inside which a tensor-core (bf16-input) similarity is not trusted and the pair
+# is re-evaluated from the fp32 rows: rows that are exactly bf16-representable only suffer fp32
+# accumulation-order noise; otherwise the bf16 rounding of the inputs dominates.
+BAND_EXACT = 1e-4
+BAND_INEXACT = 4e-3
+
+
+def select_key_frames_device(features: torch.Tensor, similarity_threshold: float = 0.9,
+                             band_exact: float = BAND_EXACT, band_inexact: float = BAND_INEXACT):
+    """Greedy redundancy filter on a device tensor (n, d) fp32, d % 64 == 0.
+
+    Returns (kept int64 [n] device tensor, count int32 [1] device tensor, stats int32 [4] device tensor);
+    only the first `count` entries of `kept` are valid.  No host synchronisation.
+    """
+    lib = _lib.load()
+    dev = _cuda.require_device(features.device)
+    if features.dtype != torch.float32 or features.dim() != 2 or not features.is_contiguous():
+        raise ValueError("features must be a contiguous fp32 (n, d) tensor")
+    n, d = features.shape
+    if d % 64:
+        raise ValueError("d must be a multiple of 64 (pad with zero columns)")
+    kept = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    stats = torch.zeros((4,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.hippo_consolidate_workspace_bytes(n, d)
+        ws = _cuda.workspace(ws_bytes, dev, "consolidate")
+        _lib.check(lib.hippo_consolidate(
+            features.data_ptr(), n, d, float(np.float32(similarity_threshold)), float(band_exact),
+            float(band_inexact), kept.data_ptr(), count.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+            _cuda.stream_ptr()))
+    return kept, count, stats
+
+
+def select_key_frames(features, times=None, similarity_threshold: float = 0.9) -> np.ndarray:
+    """Indices (ascending, int64) of the rows a greedy pass keeps: row 0, then every row whose cosine
+    similarity to ALL previously kept rows is below the threshold.  `times` is accepted and unused,
+    as in the reference (hm:944-945).  Rows are expected in time order (hm:838)."""
+    if isinstance(features, torch.Tensor):
+        n = features.shape[0]
+        if n <= 2:                                   # hm:946-947
+            return np.arange(n)
+        f = features.detach().to(torch.float32)
+    else:
+        features = np.asarray(features)
+        n = len(features)
+        if n <= 2:
+            return np.arange(n)
+        f = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+    if f.dim() != 2:
+        raise ValueError("features must be 2-D (n, d)")
+    dev = _cuda.require_device(None if not f.is_cuda else f.device)
+    d = f.shape[1]
+    d_pad = (d + 63) // 64 * 64
+    if f.is_cuda:
+        fd = f
+    else:
+        fd = _cuda.to_device(f, dev)
+    if d_pad != d:
+        fp = torch.zeros((n, d_pad), dtype=torch.float32, device=dev)
+        fp[:, :d] = fd
+        fd = fp
+    fd = fd.contiguous()
+    kept, count, _ = select_key_frames_device(fd, similarity_threshold)
+    c = int(count.item())
+    return kept[:c].cpu().numpy()

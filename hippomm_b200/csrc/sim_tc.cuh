@@ -1,0 +1,48 @@
+// Interface of the tcgen05 similarity contraction (sim_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace hippo {
+
+constexpr int kTcBM = 128;      // query / row-i block (TMEM lanes)
+constexpr int kTcBN = 256;      // bank / row-j block (TMEM columns)
+constexpr int kTcBK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+struct TcTopkArgs {
+  const void* bank;          // [n, d] bf16
+  const float* bnorm;        // [n]
+  int64_t n;
+  int d;
+  const void* qbf16;         // [nq_pad, d] bf16 (nq_pad multiple of 128 not required; TMA zero-fills)
+  const float* qnorm;        // [nq]
+  int nq;
+  int k;
+  int64_t row_base;
+  const uint64_t* after_key; // [nq] or null
+  uint64_t* part;            // [splits, nq, k]
+  uint32_t* thr_ord;         // [nq], zero-initialised by the caller
+  int splits;                // bank splits (units = m_blocks * splits)
+};
+// number of bank splits the launch will use for (n, nq) on this device
+int tc_topk_splits(int64_t n, int nq);
+hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s);
+
+struct TcMaskArgs {
+  const void* feats_bf16;    // [n, d] bf16
+  const float* norm;         // [n]
+  int64_t n;
+  int d;
+  float gamma;
+  float band_exact, band_inexact;
+  const int32_t* inexact;    // device flag from hippo_bank_build
+  uint32_t* mask;            // [n, words_per_row] bit j of row i: !(sim(i,j) < gamma), j < i
+  int64_t words_per_row;
+  uint2* uncertain;          // (i, j) pairs within the band
+  int32_t* uncertain_count;  // zero-initialised by the caller
+  int32_t uncertain_cap;
+};
+hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s);
+
+}  // namespace hippo

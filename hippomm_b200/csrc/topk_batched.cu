@@ -1,0 +1,85 @@
+// hippo_topk_batched: nq queries against the bank in one tcgen05 pass (see sim_tc.cu).
+// Reference: nq sequential calls of top_k_cosine_similarity (vo:151-188).
+#include "common.cuh"
+#include "sim_tc.cuh"
+
+namespace hippo {
+
+struct BatchedLayout {
+  __nv_bfloat16* qbf;
+  float* qnorm;
+  uint32_t* thr_ord;
+  uint64_t* part;
+  int splits;
+  size_t bytes;
+};
+
+static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d, int nq, int k) {
+  Carver c(ws, ws_bytes);
+  BatchedLayout L{};
+  L.qbf = c.take<__nv_bfloat16>((size_t)nq * d);
+  L.qnorm = c.take<float>((size_t)nq);
+  L.thr_ord = c.take<uint32_t>((size_t)nq);
+  L.splits = tc_topk_splits(n, nq);
+  L.part = c.take<uint64_t>((size_t)L.splits * nq * k);
+  L.bytes = c.used();
+  return L;
+}
+
+}  // namespace hippo
+
+extern "C" {
+
+size_t hippo_topk_batched_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k) {
+  if (n < 0 || d <= 0 || nq <= 0 || k <= 0) return 256;
+  return hippo::batched_layout(nullptr, 0, n, d, nq, k).bytes;
+}
+
+hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, int32_t d, const float* q,
+                                int32_t nq, int32_t k, int64_t row_base, const uint64_t* after_key,
+                                int64_t* out_idx, float* out_score, uint64_t* out_key, void* ws,
+                                size_t ws_bytes, void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "hippo_topk_batched: need d %% 64 == 0 (d=%d)", d);
+  HIPPO_REQUIRE(nq >= 0, "hippo_topk_batched: nq < 0");
+  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "hippo_topk_batched: k=%d outside 1..%d", k, HIPPO_TOPK_MAX);
+  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll,
+                "hippo_topk_batched: global row numbers must stay below 2^32-1");
+  if (nq == 0) return HIPPO_OK;
+  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "hippo_topk_batched: null pointer");
+  hippo_status st = check_arch();
+  if (st != HIPPO_OK) return st;
+  cudaStream_t s = (cudaStream_t)stream;
+  BatchedLayout L = batched_layout(ws, ws_bytes, n, d, nq, k);
+  if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
+    set_error("hippo_topk_batched: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
+    return HIPPO_E_WORKSPACE;
+  }
+  if (n == 0) {
+    HIPPO_CUDA(cudaMemsetAsync(L.part, 0, (size_t)nq * k * 8, s));
+    return hippo_topk_merge(L.part, 1, nq, k, k, out_idx, out_score, out_key, stream);
+  }
+  HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, (size_t)nq * 4, s));
+  // queries -> bf16 + |a| (same pass the bank went through)
+  st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
+  if (st != HIPPO_OK) return st;
+  TcTopkArgs a{};
+  a.bank = bank;
+  a.bnorm = norm;
+  a.n = n;
+  a.d = d;
+  a.qbf16 = L.qbf;
+  a.qnorm = L.qnorm;
+  a.nq = nq;
+  a.k = k;
+  a.row_base = row_base;
+  a.after_key = after_key;
+  a.part = L.part;
+  a.thr_ord = L.thr_ord;
+  a.splits = L.splits;
+  st = tc_topk_launch(a, s);
+  if (st != HIPPO_OK) return st;
+  return hippo_topk_merge(L.part, L.splits, nq, k, k, out_idx, out_score, out_key, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// hippo_topk_single / hippo_topk_merge: one-query cosine top-k over the device bank.
+//
+// Reference: top_k_cosine_similarity (vo:151-188): sims = b.a / (|b| |a|), argsort, last k
+// reversed.  Here: a bandwidth-bound GEMV.  Each warp streams groups of 4 bank rows with
+// 128-bit non-allocating loads (the bank is read exactly once), multiplies against the fp32
+// query staged in shared memory, reduces with shuffles, and keeps a warp-private top-k list
+// that only rows passing a threshold test ever touch.  Per-block lists are merged by a
+// selection pass; a second tiny kernel merges the per-block results.
+#include "common.cuh"
+
+namespace hippo {
+
+constexpr int kSingleThreads = 512;
+constexpr int kSingleWarps = kSingleThreads / 32;
+constexpr int kRowsPerIter = 4;
+
+// r-th best = largest key strictly below the previous winner; keys are unique per row.
+// cand[i * stride] for i in [0, ncand); returns 0 when nothing is left.
+__device__ __forceinline__ uint64_t warp_next_best(const uint64_t* cand, int ncand, uint64_t below,
+                                                   int lane) {
+  uint64_t best = 0;
+  for (int i = lane; i < ncand; i += 32) {
+    uint64_t c = cand[i];
+    if (c < below && c > best) best = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  return best;
+}
+
+// Filter threshold for t = dot * (1/|b|) given the current k-th best score:
+// anything that could reach `kth` after the exact IEEE evaluation must pass !(t < thr).
+__device__ __forceinline__ float filter_threshold(uint64_t kth_key, float an) {
+  if (kth_key == 0) return -INFINITY;                       // list not full yet
+  uint32_t ord = (uint32_t)(kth_key >> 32);
+  if (ord == 0xffffffffu) return INFINITY;                  // k NaNs already: only NaN/inf pass
+  float lo = ord_to_score(ord) * an;
+  return lo - fabsf(lo) * 9.5367431640625e-07f - 1e-37f;    // 2^-20 relative slack
+}
+
+template <int CH>  // CH = d/256 when d is a multiple of 256 and <= 4*256; 0 = generic
+__global__ void __launch_bounds__(kSingleThreads, 2)
+topk_single_kernel(const __nv_bfloat16* __restrict__ bank, const float* __restrict__ norm, int64_t n,
+                   int d, const float* __restrict__ q, int k, int64_t row_base,
+                   const uint64_t* __restrict__ after_key, uint64_t* __restrict__ part /*[grid][k]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // query, permuted so that a lane's two float4 loads are conflict free:
+  // element e = c*256 + lane*8 + h*4 + j  ->  sq[((c*2 + h)*32 + lane)*4 + j]
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  const int dpad = (d + 255) / 256 * 256;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dpad * 4);  // [warps][k]
+  __shared__ float s_an;
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  // stage query, compute |a| the way the reference does (fp32 sqrt of the sum of squares)
+  double ss = 0.0;
+  for (int e = threadIdx.x; e < dpad; e += blockDim.x) {
+    float v = e < d ? q[e] : 0.f;
+    ss += (double)v * (double)v;
+    int c = e >> 8, l = (e >> 3) & 31, h = (e >> 2) & 1, j = e & 3;
+    sq[(((c * 2 + h) * 32) + l) * 4 + j] = v;
+  }
+  ss = warp_sum(ss);
+  __shared__ double s_part[kSingleWarps];
+  if (lane == 0) s_part[wid] = ss;
+  for (int i = lane; i < k; i += 32) lists[wid * k + i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kSingleWarps; ++i) t += s_part[i];
+    s_an = __fsqrt_rn((float)t);
+  }
+  __syncthreads();
+  const float an = s_an;
+  const uint64_t below = after_key ? after_key[0] : ~0ull;
+  uint64_t* mylist = lists + wid * k;
+  float thr = -INFINITY;
+
+  const int chunks = dpad >> 8;
+  const int64_t ngroups = (n + kRowsPerIter - 1) / kRowsPerIter;
+  const int64_t gwarp = (int64_t)blockIdx.x * kSingleWarps + wid;
+  const int64_t gstride = (int64_t)gridDim.x * kSingleWarps;
+
+  for (int64_t g = gwarp; g < ngroups; g += gstride) {
+    const int64_t r0 = g * kRowsPerIter;
+    float acc[kRowsPerIter];
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) acc[r] = 0.f;
+    const __nv_bfloat16* rp[kRowsPerIter];
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) {
+      int64_t row = r0 + r < n ? r0 + r : n - 1;
+      rp[r] = bank + row * (int64_t)d + lane * 8;
+    }
+    if constexpr (CH > 0) {
+      uint4 w[CH][kRowsPerIter];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int r = 0; r < kRowsPerIter; ++r) w[c][r] = ldg_stream(rp[r] + c * 256);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float4 qa = *reinterpret_cast<const float4*>(&sq[((c * 2 + 0) * 32 + lane) * 4]);
+        const float4 qb = *reinterpret_cast<const float4*>(&sq[((c * 2 + 1) * 32 + lane) * 4]);
+#pragma unroll
+        for (int r = 0; r < kRowsPerIter; ++r) {
+          const uint4 x = w[c][r];
+          float a = acc[r];
+          a = fmaf(bf16lo(x.x), qa.x, a); a = fmaf(bf16hi(x.x), qa.y, a);
+          a = fmaf(bf16lo(x.y), qa.z, a); a = fmaf(bf16hi(x.y), qa.w, a);
+          a = fmaf(bf16lo(x.z), qb.x, a); a = fmaf(bf16hi(x.z), qb.y, a);
+          a = fmaf(bf16lo(x.w), qb.z, a); a = fmaf(bf16hi(x.w), qb.w, a);
+          acc[r] = a;
+        }
+      }
+    } else {
+      for (int c = 0; c < chunks; ++c) {
+        if (c * 256 + lane * 8 < d) {
+          const float4 qa = *reinterpret_cast<const float4*>(&sq[((c * 2 + 0) * 32 + lane) * 4]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sq[((c * 2 + 1) * 32 + lane) * 4]);
+          uint4 w[kRowsPerIter];
+#pragma unroll
+          for (int r = 0; r < kRowsPerIter; ++r) w[r] = ldg_stream(rp[r] + c * 256);
+#pragma unroll
+          for (int r = 0; r < kRowsPerIter; ++r) {
+            const uint4 x = w[r];
+            float a = acc[r];
+            a = fmaf(bf16lo(x.x), qa.x, a); a = fmaf(bf16hi(x.x), qa.y, a);
+            a = fmaf(bf16lo(x.y), qa.z, a); a = fmaf(bf16hi(x.y), qa.w, a);
+            a = fmaf(bf16lo(x.z), qb.x, a); a = fmaf(bf16hi(x.z), qb.y, a);
+            a = fmaf(bf16lo(x.w), qb.z, a); a = fmaf(bf16hi(x.w), qb.w, a);
+            acc[r] = a;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) acc[r] = warp_sum(acc[r]);
+
+    // lane r owns row r0 + r
+    float dot = acc[0];
+#pragma unroll
+    for (int r = 1; r < kRowsPerIter; ++r) dot = lane == r ? acc[r] : dot;
+    const int64_t row = r0 + lane;
+    bool cand = false;
+    float bn = 0.f;
+    if (lane < kRowsPerIter && row < n) {
+      bn = norm[row];
+      float t = dot * __frcp_rn(bn);
+      cand = !(t < thr);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      if (lane == src) {
+        // the reference's operation order: dot / (|b| * |a|), IEEE fp32 (vo:182)
+        float s = __fdiv_rn(dot, __fmul_rn(bn, an));
+        uint64_t key = pack_key(s, (uint32_t)(row_base + row));
+        if (key < below && key > mylist[k - 1]) topk_insert(mylist, k, key);
+      }
+      __syncwarp();
+      thr = filter_threshold(mylist[k - 1], an);
+    }
+  }
+  __syncthreads();
+  // block merge: warp 0 selects the k best of kSingleWarps * k candidates
+  if (wid == 0) {
+    uint64_t prev = ~0ull;
+    for (int r = 0; r < k; ++r) {
+      uint64_t b = warp_next_best(lists, kSingleWarps * k, prev, lane);
+      if (lane == 0) part[(size_t)blockIdx.x * k + r] = b;
+      prev = b ? b : 0;  // once empty, stays empty
+      if (b == 0) prev = 0;
+    }
+  }
+}
+
+// keys [nparts, nq, k_in] -> best k per query; one warp per query.
+__global__ void __launch_bounds__(128) topk_merge_kernel(const uint64_t* __restrict__ keys, int nparts,
+                                                         int nq, int k_in, int k,
+                                                         int64_t* __restrict__ out_idx,
+                                                         float* __restrict__ out_score,
+                                                         uint64_t* __restrict__ out_key) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  uint64_t prev = ~0ull;
+  for (int r = 0; r < k; ++r) {
+    uint64_t best = 0;
+    if (prev != 0) {
+      for (int i = lane; i < nparts * k_in; i += 32) {
+        int p = i / k_in, j = i - p * k_in;
+        uint64_t c = keys[((size_t)p * nq + qi) * k_in + j];
+        if (c < prev && c > best) best = c;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+    }
+    if (lane == 0) {
+      size_t o = (size_t)qi * k + r;
+      if (out_idx) out_idx[o] = best ? (int64_t)key_row(best) : -1;
+      if (out_score) out_score[o] = best ? key_score(best) : 0.f;
+      if (out_key) out_key[o] = best;
+    }
+    prev = best;
+  }
+}
+
+static size_t single_smem_bytes(int d, int k) {
+  return (size_t)((d + 255) / 256 * 256) * 4 + (size_t)kSingleWarps * k * 8;
+}
+static int single_grid(int64_t n) {
+  int64_t groups = (n + kRowsPerIter - 1) / kRowsPerIter;
+  int64_t want = (groups + kSingleWarps - 1) / kSingleWarps;
+  int64_t cap = (int64_t)sm_count() * 2;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace hippo
+
+extern "C" {
+
+size_t hippo_topk_single_workspace_bytes(int64_t n, int32_t d, int32_t k) {
+  (void)d;
+  int sms = hippo::sm_count();
+  if (sms <= 0) sms = 148;
+  (void)n;
+  return hippo::align_up((size_t)sms * 2 * (size_t)(k > 0 ? k : 1) * 8, 256);
+}
+
+hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, int32_t k_in,
+                              int32_t k, int64_t* out_idx, float* out_score, uint64_t* out_key,
+                              void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(nparts >= 1 && nq >= 0 && k_in >= 1 && k >= 1, "hippo_topk_merge: bad sizes");
+  if (nq == 0) return HIPPO_OK;
+  HIPPO_REQUIRE(keys != nullptr, "hippo_topk_merge: null keys");
+  hippo_status st = check_arch();
+  if (st != HIPPO_OK) return st;
+  int blocks = (nq + 3) / 4;
+  topk_merge_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(keys, nparts, nq, k_in, k, out_idx,
+                                                              out_score, out_key);
+  HIPPO_CUDA(cudaGetLastError());
+  return HIPPO_OK;
+}
+
+hippo_status hippo_topk_single(const void* bank, const float* norm, int64_t n, int32_t d,
+                               const float* q, int32_t k, int64_t row_base,
+                               const uint64_t* after_key, int64_t* out_idx, float* out_score,
+                               uint64_t* out_key, void* ws, size_t ws_bytes, void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "hippo_topk_single: need d %% 64 == 0 (d=%d)", d);
+  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "hippo_topk_single: k=%d outside 1..%d", k,
+                HIPPO_TOPK_MAX);
+  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll,
+                "hippo_topk_single: global row numbers must stay below 2^32-1");
+  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "hippo_topk_single: null pointer");
+  hippo_status st = check_arch();
+  if (st != HIPPO_OK) return st;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = single_grid(n);
+  if (ws == nullptr || ws_bytes < (size_t)grid * k * 8 || ((uintptr_t)ws & 255)) {
+    set_error("hippo_topk_single: workspace of %zu bytes needed (256-byte aligned)",
+              hippo_topk_single_workspace_bytes(n, d, k));
+    return HIPPO_E_WORKSPACE;
+  }
+  uint64_t* part = (uint64_t*)ws;
+  if (n == 0) {
+    HIPPO_CUDA(cudaMemsetAsync(part, 0, (size_t)k * 8, s));
+    return hippo_topk_merge(part, 1, 1, k, k, out_idx, out_score, out_key, stream);
+  }
+  const size_t smem = single_smem_bytes(d, k);
+  HIPPO_REQUIRE(smem <= 200 * 1024, "hippo_topk_single: d=%d too large", d);
+  const __nv_bfloat16* b = (const __nv_bfloat16*)bank;
+  if (d == 1024) {
+    static bool attr4 = false;
+    if (!attr4) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr4 = true; }
+    topk_single_kernel<4><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part);
+  } else {
+    static bool attr0 = false;
+    if (!attr0) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0 = true; }
+    topk_single_kernel<0><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part);
+  }
+  HIPPO_CUDA(cudaGetLastError());
+  return hippo_topk_merge(part, grid, 1, k, k, out_idx, out_score, out_key, stream);
+}
+
+}  // extern "C"

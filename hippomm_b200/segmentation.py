@@ -1,0 +1,287 @@
+"""Temporal pattern separation: drop-ins for HippocampalMemory._segment_sequence (hm:1002-1114),
+_compute_frame_similarity (hm:980-991), _compute_audio_level (hm:993-1000) and
+batch_process.compute_frame_difference (bp:32-71).
+
+Host code only decodes files and slices Python lists; every arithmetic step (gray conversion,
+SSIM / MSE, RMS levels, the boundary state machine) runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cuda, _lib
+
+_PCM_ENUM = {torch.int16: _lib.HIPPO_I16, torch.float32: _lib.HIPPO_F32, torch.float64: _lib.HIPPO_F64}
+
+
+@dataclass
+class SequenceSegment:
+    """Same fields as the reference dataclass (hm:35-42)."""
+    start_time: float
+    end_time: float
+    frames: Optional[List[str]] = None
+    audio_data: Optional[np.ndarray] = None
+    frame_times: Optional[List[float]] = None
+
+
+# ------------------------------------------------------------------ frames ----
+def _load_frames(video_frames: Sequence) -> np.ndarray:
+    """Paths (decoded with cv2 like hm:982-983) or arrays -> one uint8 array [n, h, w, ch]."""
+    if isinstance(video_frames, np.ndarray) and video_frames.ndim in (3, 4) and video_frames.dtype == np.uint8:
+        arr = video_frames if video_frames.ndim == 4 else video_frames[..., None]
+        return np.ascontiguousarray(arr)
+    imgs = []
+    for f in video_frames:
+        if isinstance(f, np.ndarray):
+            img = f
+        else:
+            import cv2  # decode only; all arithmetic happens on the GPU
+            img = cv2.imread(str(f))
+            if img is None:
+                raise ValueError(f"could not read frame {f!r}")
+        if img.dtype != np.uint8:
+            raise ValueError("frames must be uint8")
+        if img.ndim == 2:
+            img = img[..., None]
+        imgs.append(img)
+    shape = imgs[0].shape
+    for img in imgs:
+        if img.shape != shape:
+            # skimage raises for a pair of different shapes (hm:990); a stream mixes none
+            raise ValueError("Input images must have the same dimensions.")
+    return np.ascontiguousarray(np.stack(imgs))
+
+
+def frame_pair_scores_device(frames: torch.Tensor, pair_a: Optional[torch.Tensor] = None,
+                             pair_b: Optional[torch.Tensor] = None, range_mode: int = 0):
+    """frames uint8 [n, h, w, ch] on the device -> (ssim fp64 [np], mse fp64 [np]) device tensors.
+    Without explicit pairs, pair p is (frame p+1, frame p), the order hm:1052-1056 scans them."""
+    lib = _lib.load()
+    dev = _cuda.require_device(frames.device)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_contiguous():
+        raise ValueError("frames must be a contiguous uint8 [n, h, w, ch] tensor")
+    n, h, w, ch = frames.shape
+    if pair_a is None:
+        npairs = n - 1
+        pa = pb = None
+    else:
+        pa = pair_a.to(dev, torch.int32).contiguous()
+        pb = pair_b.to(dev, torch.int32).contiguous()
+        npairs = pa.numel()
+    ssim = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
+    mse = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
+    if npairs > 0:
+        with torch.cuda.device(dev):
+            ws_bytes = lib.hippo_frame_pairs_workspace_bytes(n, h, w, npairs)
+            ws = _cuda.workspace(ws_bytes, dev, "frames")
+            _lib.check(lib.hippo_frame_pairs(
+                frames.data_ptr(), n, h, w, ch, _cuda.ptr(pa), _cuda.ptr(pb), npairs, range_mode,
+                ssim.data_ptr(), mse.data_ptr(), ws.data_ptr(), ws.numel(), _cuda.stream_ptr()))
+    return ssim[:npairs], mse[:npairs]
+
+
+def compute_frame_similarity(frame1, frame2) -> float:
+    """Mean SSIM of two frames given as paths or BGR arrays (hm:980-991)."""
+    frames = _load_frames([frame1, frame2])
+    if frames.shape[1] < 7 or frames.shape[2] < 7:
+        raise ValueError("win_size exceeds image extent. Either ensure that your images are at least 7x7; "
+                         "or pass win_size explicitly in the function call, with an odd value less than or "
+                         "equal to the smaller side of your images.")
+    dev = _cuda.require_device()
+    fd = _cuda.to_device(frames, dev)
+    a = torch.tensor([0], dtype=torch.int32)
+    b = torch.tensor([1], dtype=torch.int32)
+    ssim, _ = frame_pair_scores_device(fd, a, b, range_mode=0)
+    return float(ssim.item())
+
+
+def compute_frame_difference(frame1: np.ndarray, frame2: np.ndarray) -> float:
+    """1 - SSIM of the frames scaled to [0, 1]; MSE fallback when SSIM is not finite (bp:32-71)."""
+    f1 = np.asarray(frame1)
+    f2 = np.asarray(frame2)
+    c1 = 1 if f1.ndim == 2 else f1.shape[2]
+    c2 = 1 if f2.ndim == 2 else f2.shape[2]
+    if c1 != c2:
+        raise NotImplementedError("compute_frame_difference: frames with different channel counts")
+    frames = _load_frames([f1, f2])
+    dev = _cuda.require_device()
+    fd = _cuda.to_device(frames, dev)
+    a = torch.tensor([0], dtype=torch.int32)
+    b = torch.tensor([1], dtype=torch.int32)
+    ssim, mse = frame_pair_scores_device(fd, a, b, range_mode=1)
+    vals = torch.stack([ssim[0], mse[0]]).cpu().numpy()
+    score, mse_v = float(vals[0]), float(vals[1])
+    if frames.shape[1] >= 7 and frames.shape[2] >= 7 and np.isfinite(score):   # bp:59-63
+        return 1.0 - score
+    return min(1.0, mse_v)                                                     # bp:67-71
+
+
+# ------------------------------------------------------------------- audio ----
+def _audio_to_device(audio_data, dev):
+    """Host audio (n,) / (n, ch) of int16 / float32 / float64 -> device tensor in its own dtype."""
+    if isinstance(audio_data, torch.Tensor):
+        t = audio_data.detach()
+        if t.dtype not in _PCM_ENUM:
+            t = t.to(torch.float64)
+        t = t.to(dev, non_blocking=True)
+    else:
+        a = np.asarray(audio_data)
+        if a.dtype not in (np.int16, np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = _cuda.to_device(a, dev)
+    if t.dim() == 1:
+        t = t.reshape(-1, 1)
+    if t.dim() != 2:
+        raise ValueError("audio_data must be (n,) or (n, channels)")
+    return t.contiguous()
+
+
+def audio_energy_device(pcm: torch.Tensor):
+    """pcm [ns, nch] device tensor -> (e16 fp64 [ceil(ns/16)], e512 fp64 [ceil(ns/512)])."""
+    lib = _lib.load()
+    dev = _cuda.require_device(pcm.device)
+    ns, nch = pcm.shape
+    e16 = torch.empty((max((ns + 15) // 16, 1),), dtype=torch.float64, device=dev)
+    e512 = torch.empty((max((ns + 511) // 512, 1),), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hippo_audio_energy(pcm.data_ptr(), _PCM_ENUM[pcm.dtype], ns, nch, e16.data_ptr(),
+                                          e512.data_ptr(), _cuda.stream_ptr()))
+    return e16, e512
+
+
+def audio_levels_device(pcm: torch.Tensor, win_start: torch.Tensor, win_len: torch.Tensor, pyramid=None):
+    """RMS level in dB of windows [start, start+len) of a device pcm [ns, nch]; fp64 [nwin] device tensor."""
+    lib = _lib.load()
+    dev = _cuda.require_device(pcm.device)
+    ns, nch = pcm.shape
+    ws_ = win_start.to(dev, torch.int64).contiguous()
+    wl_ = win_len.to(dev, torch.int64).contiguous()
+    out = torch.empty((max(ws_.numel(), 1),), dtype=torch.float64, device=dev)
+    e16, e512 = pyramid if pyramid is not None else (None, None)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hippo_audio_levels(pcm.data_ptr(), _PCM_ENUM[pcm.dtype], ns, nch, _cuda.ptr(e16),
+                                          _cuda.ptr(e512), ws_.data_ptr(), wl_.data_ptr(), ws_.numel(),
+                                          out.data_ptr(), _cuda.stream_ptr()))
+    return out[: ws_.numel()]
+
+
+def compute_audio_level(audio_data, sample_rate=None) -> float:
+    """RMS level of an audio segment in dB, -100 for digital silence (hm:993-1000). `sample_rate` is unused."""
+    dev = _cuda.require_device()
+    pcm = _audio_to_device(audio_data, dev)
+    n = pcm.shape[0]
+    lv = audio_levels_device(pcm, torch.tensor([0], dtype=torch.int64), torch.tensor([n], dtype=torch.int64))
+    return float(lv.item())
+
+
+# ------------------------------------------------------------ segmentation ----
+def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],
+                              pcm: Optional[torch.Tensor], pyramid, sample_rate, max_segment_duration: float,
+                              min_segment_duration: float, frame_similarity_threshold: float,
+                              audio_silence_threshold: float, max_segments: int):
+    """One stream through hippo_segment_boundaries. Returns (bounds fp64 [max_segments, 2], count int32 [1])."""
+    lib = _lib.load()
+    ref = frame_times if frame_times is not None else pcm
+    dev = _cuda.require_device(ref.device)
+    bounds = torch.empty((max_segments, 2), dtype=torch.float64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    desc = _lib.StreamDesc()
+    desc.ssim = _cuda.ptr(ssim) if ssim is not None and ssim.numel() > 0 else None
+    desc.frame_times = _cuda.ptr(frame_times)
+    desc.nframes = 0 if frame_times is None else frame_times.numel()
+    desc.pcm = _cuda.ptr(pcm)
+    desc.e16 = None if pyramid is None else pyramid[0].data_ptr()
+    desc.e512 = None if pyramid is None else pyramid[1].data_ptr()
+    desc.ns = 0 if pcm is None else pcm.shape[0]
+    desc.nch = 1 if pcm is None else pcm.shape[1]
+    desc.pcm_dtype = _lib.HIPPO_F64 if pcm is None else _PCM_ENUM[pcm.dtype]
+    desc.sample_rate = float(sample_rate) if sample_rate else 0.0
+    desc.out_bounds = bounds.data_ptr()
+    desc.out_count = count.data_ptr()
+    desc.max_segments = max_segments
+    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(desc), ctypes.sizeof(desc)), dtype=np.uint8).copy()
+    desc_dev = torch.from_numpy(raw).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hippo_segment_boundaries(
+            desc_dev.data_ptr(), 1, float(max_segment_duration), float(min_segment_duration),
+            float(frame_similarity_threshold), float(audio_silence_threshold), _cuda.stream_ptr()))
+    return bounds, count
+
+
+def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio_sample_rate=None, *,
+                     max_segment_duration: float = 30.0, min_segment_duration: float = 10.0,
+                     frame_similarity_threshold: float = 0.95, audio_silence_threshold: float = -40,
+                     ) -> List[SequenceSegment]:
+    """Drop-in for HippocampalMemory._segment_sequence (hm:1002-1114); thresholds default to
+    config/default_config.yaml:27-30.  `video_frames` may be paths (as in the reference), BGR arrays,
+    or one uint8 array [n, h, w, 3]."""
+    segments: List[SequenceSegment] = []
+    if video_frames is None and audio_data is None:                                   # hm:1024-1025
+        return segments
+    has_video = (video_frames is not None and len(video_frames) > 0
+                 and frame_times is not None and len(frame_times) > 0)
+    has_audio = audio_data is not None and bool(audio_sample_rate)
+    if has_video:                                                                     # hm:1027-1032
+        total = frame_times[-1] - frame_times[0]
+    elif has_audio:
+        total = len(audio_data) / audio_sample_rate
+    else:
+        return segments
+    if not (total > 0.0):
+        return segments
+    if not (min_segment_duration > 0):
+        raise ValueError("min_segment_duration must be positive (the reference loop would not terminate)")
+    dev = _cuda.require_device()
+
+    ssim_d = ft_d = None
+    if has_video:
+        ft = np.asarray(frame_times, dtype=np.float64)
+        if len(video_frames) != len(ft):
+            raise ValueError("video_frames and frame_times differ in length")
+        if np.any(np.diff(ft) < 0):
+            raise ValueError("frame_times must be non-decreasing")
+        ft_d = _cuda.to_device(ft, dev)
+        if len(ft) > 1:
+            if isinstance(video_frames, torch.Tensor):
+                frames_d = video_frames.to(dev).contiguous()
+            else:
+                frames_d = _cuda.to_device(_load_frames(video_frames), dev)
+            if frames_d.shape[1] < 7 or frames_d.shape[2] < 7:
+                raise ValueError("win_size exceeds image extent.")
+            ssim_d, _ = frame_pair_scores_device(frames_d, range_mode=0)
+    pcm_d = pyr = None
+    if has_audio:
+        if int(0.5 * audio_sample_rate) < 1:
+            raise ValueError("range() arg 3 must not be zero")                      # hm:1068 with a tiny rate
+        pcm_d = _audio_to_device(audio_data, dev)
+        pyr = audio_energy_device(pcm_d)
+
+    max_segments = int(math.ceil(total / min_segment_duration)) + 2
+    bounds, count = segment_boundaries_device(
+        ssim_d, ft_d, pcm_d, pyr, audio_sample_rate, max_segment_duration, min_segment_duration,
+        frame_similarity_threshold, audio_silence_threshold, max_segments)
+    c = int(count.item())
+    if c < 0:
+        raise RuntimeError("segment table overflow")
+    b = bounds[:c].cpu().numpy()
+
+    # hm:1087-1108: attach the frames / audio of each segment (list slicing, host side)
+    ft_list = list(frame_times) if has_video else None
+    for i in range(c):
+        cs, opt = float(b[i, 0]), float(b[i, 1])
+        seg = SequenceSegment(start_time=cs, end_time=opt)
+        if has_video:
+            seg.frames = [f for f, t in zip(video_frames, ft_list) if cs <= t <= opt]
+            seg.frame_times = [t for t in ft_list if cs <= t <= opt]
+        if has_audio:
+            s0 = int(cs * audio_sample_rate)
+            s1 = int(opt * audio_sample_rate)
+            seg.audio_data = audio_data[s0:s1]
+        segments.append(seg)
+    return segments

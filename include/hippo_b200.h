@@ -1,0 +1,221 @@
+/*
+ * hippo_b200.h — C ABI of libhippo_b200.so
+ *
+ * B200 (sm_100a) implementation of HippoMM's data-parallel memory hot path.
+ * Every entry point replaces (part of) one plain-Python call site of the
+ * reference; the file:line each one stands in for is cited on the declaration
+ * (paths relative to the reference checkout, `hm` = hippomm/core/
+ * hippocampal_memory.py, `bp` = hippomm/core/batch_process.py, `vo` =
+ * hippomm/utils/vector_ops.py).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *     The caller (PyTorch) owns every buffer; nothing is allocated inside a
+ *     hot call.  Scratch comes in through (ws, ws_bytes); ask the matching
+ *     *_workspace_bytes() for the size.  Workspaces need 256-byte alignment.
+ *   - Every call takes the cudaStream_t to launch on (as void*), is
+ *     asynchronous with respect to the host and is reentrant across streams
+ *     as long as workspaces are not shared.
+ *   - Every call returns a hippo_status (0 = OK, <0 = error); the message of
+ *     the last error on the calling thread is hippo_last_error().
+ *   - There is no CPU fallback: on a device that is not sm_100 the compute
+ *     calls return HIPPO_E_ARCH.
+ */
+#ifndef HIPPO_B200_H_
+#define HIPPO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIPPO_ABI_VERSION 1
+
+typedef int32_t hippo_status;
+#define HIPPO_OK           0
+#define HIPPO_E_BADARG    (-1)  /* null pointer, bad size, bad enum            */
+#define HIPPO_E_ARCH      (-2)  /* current device is not sm_100                */
+#define HIPPO_E_CUDA      (-3)  /* a CUDA runtime / driver call failed         */
+#define HIPPO_E_NCCL      (-4)  /* reserved (collectives live on the torch side)*/
+#define HIPPO_E_WORKSPACE (-5)  /* workspace missing / too small / misaligned  */
+
+/* element types of caller-provided rows / samples */
+#define HIPPO_F32  0
+#define HIPPO_F64  1
+#define HIPPO_BF16 2
+#define HIPPO_I16  3
+
+/* Largest k one search launch keeps per query (larger k: the host wrapper
+ * calls again with the `after_*` cursor, see hippo_topk_*).                 */
+#define HIPPO_TOPK_MAX 32
+
+/* ---- library ------------------------------------------------------------ */
+int32_t      hippo_abi_version(void);
+const char*  hippo_last_error(void);
+/* HIPPO_OK iff the CURRENT device can run the kernels (compute capability 10.x). */
+hippo_status hippo_device_check(void);
+/* Number of SMs of the current device (grid sizing on the host side). */
+int32_t      hippo_sm_count(void);
+
+/* ---- memory bank -------------------------------------------------------- */
+/*
+ * Build the device-resident bank from caller rows: bf16 copy of the rows plus
+ * the fp32 L2 norm of every ORIGINAL row.  Replaces the per-query
+ * `np.linalg.norm(b, axis=1)` of vo:179 (97 % of the reference's search time)
+ * and the row normalisation of hm:951.
+ *   rows      [n, d] of `dtype` (HIPPO_F32 / HIPPO_F64 / HIPPO_BF16), row stride `ld` elements
+ *   bank      [n, d] bf16 out (row stride d), d % 64 == 0 (host zero-pads)
+ *   norm      [n] fp32 out, ||row||_2 (sqrt of the fp32-rounded sum of squares)
+ *   inexact   optional int32*: OR-ed with 1 if any element changed when rounded to bf16
+ */
+hippo_status hippo_bank_build(const void* rows, int32_t dtype, int64_t n, int32_t d, int64_t ld,
+                              void* bank, float* norm, int32_t* inexact, void* stream);
+
+/* ---- detailed-recall feature search (vo:151-188, callers hm:3153, hm:3304) */
+/*
+ * Search results are (score, row) pairs ordered by score descending; ties
+ * are broken by LOWER row first (the reference's argsort leaves ties
+ * unordered); NaN scores (zero-norm rows) sort above every number exactly as
+ * `np.argsort` puts them last (vo:185).  score = dot / (norm_b * norm_a) in
+ * fp32 with IEEE division, the operation order of vo:182.
+ *
+ *   bank/norm   from hippo_bank_build, n rows of d
+ *   q           query vector(s) in fp32, [nq, d], row stride d
+ *   k           1..HIPPO_TOPK_MAX
+ *   row_base    added to local row numbers in out_idx (shard offset)
+ *   after_key   optional uint64[nq] cursor: only rows ordered strictly AFTER
+ *               this packed (score,row) key are considered (NULL = all rows).
+ *               Pass out_key of the previous call to page through k > 32.
+ *   out_idx     [nq, k] int64, -1 where fewer than k rows qualify
+ *   out_score   [nq, k] fp32
+ *   out_key     optional [nq, k] uint64 packed order keys (0 = empty slot);
+ *               this is also the payload ranks exchange for the sharded merge
+ */
+size_t       hippo_topk_single_workspace_bytes(int64_t n, int32_t d, int32_t k);
+/* One query: bandwidth-bound GEMV + warp-level top-k (north_star "single-query search"). */
+hippo_status hippo_topk_single(const void* bank, const float* norm, int64_t n, int32_t d,
+                               const float* q, int32_t k, int64_t row_base,
+                               const uint64_t* after_key,
+                               int64_t* out_idx, float* out_score, uint64_t* out_key,
+                               void* ws, size_t ws_bytes, void* stream);
+
+size_t       hippo_topk_batched_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k);
+/* nq queries at once: tcgen05 similarity contraction with the top-k fused into the
+ * TMEM epilogue (north_star "batched search").  The reference issues nq
+ * sequential vo:151 calls. */
+hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, int32_t d,
+                                const float* q, int32_t nq, int32_t k, int64_t row_base,
+                                const uint64_t* after_key,
+                                int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Merge per-shard results: keys [nparts, nq, k_in] packed order keys (as written to
+ * out_key, rows already global because every shard passed its row_base) ->
+ * the k best per query.  Runs after the all-gather of the sharded search
+ * (SURVEY §8e); also used inside the single-GPU kernels' final stage.
+ */
+hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, int32_t k_in,
+                              int32_t k, int64_t* out_idx, float* out_score, uint64_t* out_key,
+                              void* stream);
+
+/* ---- memory consolidation (hm:944-967 _select_key_frames) --------------- */
+/*
+ * Greedy redundancy filter: row 0 is kept; row i is kept iff
+ * cos(row i, row j) < gamma for every kept j < i (hm:958-961).  gamma is
+ * compared in fp32 like NumPy does for an fp32 matrix and a Python float.
+ * The similarity contraction runs on tcgen05 over the strict lower triangle
+ * only and leaves a bit matrix (never the fp32 matrix); pairs whose
+ * tensor-core similarity is within `band` of gamma are re-evaluated from the
+ * fp32 rows before the greedy scan.
+ *   feats      [n, d] fp32 rows (time-ordered), row stride d, d % 64 == 0
+ *   out_keep   [n] int64 kept row numbers ascending (first *out_count valid)
+ *   out_count  int32* (device)
+ *   out_stats  optional int32[4] (device): {pairs re-evaluated, recheck overflow,
+ *              bf16-inexact flag, reserved}
+ */
+size_t       hippo_consolidate_workspace_bytes(int64_t n, int32_t d);
+hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float gamma,
+                               float band_exact, float band_inexact,
+                               int64_t* out_keep, int32_t* out_count, int32_t* out_stats,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/* ---- temporal pattern separation ---------------------------------------- */
+/*
+ * Frame-pair scoring: BGR -> gray (cv2's fixed-point BGR2GRAY) -> mean SSIM
+ * (7x7 uniform window, K1=.01, K2=.03, sample covariance: the scikit-image
+ * defaults the reference relies on) and the MSE of the gray frames.
+ * Replaces hm:980-991 (_compute_frame_similarity; range_mode 0: data_range =
+ * max-min of the FIRST frame of the pair, in uint8) and bp:32-71
+ * (compute_frame_difference; range_mode 1: frames scaled to [0,1],
+ * data_range 1.0).
+ *   frames     [nf, h, w, ch] uint8, ch = 3 (BGR) or 1 (gray), densely packed
+ *   pair_a/b   [np] int32 frame numbers; pair p scores (frames[a], frames[b]);
+ *              NULL = adjacent pairs (p+1, p) for p in [0, nf-1) as hm:1052-1056 scans them
+ *   out_ssim   [np] fp64 mean SSIM (NaN where the reference yields NaN)
+ *   out_mse    [np] fp64 mean squared gray difference on the [0,1] scale (bp:67)
+ */
+size_t       hippo_frame_pairs_workspace_bytes(int32_t nf, int32_t h, int32_t w, int32_t npairs);
+hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int32_t w, int32_t ch,
+                               const int32_t* pair_a, const int32_t* pair_b, int32_t npairs,
+                               int32_t range_mode, double* out_ssim, double* out_mse,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Audio energy pyramid: per-sample mono x^2 summed in fp64 over blocks of 16
+ * and of 512 samples, so that any window's sum of squares (hm:993-1000) is a
+ * short exact sum instead of a fresh pass over the samples.
+ *   pcm      [ns, nch] of `dtype` (HIPPO_I16 -> x = k/32768; HIPPO_F32; HIPPO_F64)
+ *   out_e16  [ceil(ns/16)] fp64, out_e512 [ceil(ns/512)] fp64
+ */
+hippo_status hippo_audio_energy(const void* pcm, int32_t dtype, int64_t ns, int32_t nch,
+                                double* out_e16, double* out_e512, void* stream);
+
+/*
+ * RMS level in dB of arbitrary windows [start, start+len) (hm:993-1000), from the pyramid.
+ *   out_db [nwin] fp64: 20*log10(sqrt(mean x^2)), -100 when the window is all zero
+ */
+hippo_status hippo_audio_levels(const void* pcm, int32_t dtype, int64_t ns, int32_t nch,
+                                const double* e16, const double* e512,
+                                const int64_t* win_start, const int64_t* win_len, int32_t nwin,
+                                double* out_db, void* stream);
+
+/*
+ * The boundary state machine of hm:1034-1111, operation for operation in
+ * fp64, for `nstreams` independent streams (one warp each).
+ * Per stream s (all arrays indexed by the stream's offsets):
+ *   ssim        adjacent-pair SSIM, pair p = (frame p+1, frame p); NULL = no video
+ *   frame_times fp64 [nframes], non-decreasing
+ *   pcm/e16/e512 as above; NULL pcm = no audio
+ *   out_bounds  [max_segments, 2] fp64 (start, end); out_count int32
+ * Streams are described by a device array of hippo_stream_desc.
+ */
+typedef struct hippo_stream_desc {
+  const double*  ssim;         /* [nframes-1] or NULL */
+  const double*  frame_times;  /* [nframes]   or NULL */
+  int64_t        nframes;
+  const void*    pcm;          /* [ns, nch]   or NULL */
+  const double*  e16;
+  const double*  e512;
+  int64_t        ns;
+  int32_t        nch;
+  int32_t        pcm_dtype;
+  double         sample_rate;  /* audio_sample_rate as the reference receives it */
+  double*        out_bounds;   /* [max_segments, 2] */
+  int32_t*       out_count;    /* segments written; -needed if max_segments was too small */
+  int32_t        max_segments;
+  int32_t        reserved;
+} hippo_stream_desc;
+
+hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t nstreams,
+                                      double max_segment_duration, double min_segment_duration,
+                                      double frame_similarity_threshold,
+                                      double audio_silence_threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPPO_B200_H_ */

@@ -1,0 +1,120 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference functions (imported from
+/root/reference through oracle/reference_shim.py) on seeded synthetic inputs.
+
+    python tests/golden/make_golden.py
+
+Run in the build container only (the reference checkout does not exist on the GPU box).  Inputs
+are regenerated from their seeds by tests/cases.py, so only the reference's OUTPUTS are stored.
+SSIM-dependent outputs come from the reference's own call sites running on the restated
+structural_similarity (scikit-image is absent: those entries are "vs restated oracle").
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cases  # noqa: E402  (tests/cases.py)
+from oracle import reference_shim  # noqa: E402
+
+
+def main() -> None:
+    ref = reference_shim.load()
+    mem = ref.make_memory()
+    out = {}
+
+    # ---- feature search, config 1: 2,000 video-like rows, 64 planted queries, k = 5 ----
+    bank, queries = cases.search_config1()
+    idx = np.empty((len(queries), 5), dtype=np.int64)
+    sim = np.empty((len(queries), 5), dtype=np.float32)
+    for i, q in enumerate(queries):
+        idx[i], sim[i] = ref.top_k_cosine_similarity(q, bank, 5)
+    out["search_c1_idx"], out["search_c1_sim"] = idx, sim
+
+    # ---- feature search, lattice bank (bit-exact scores expected), k = 10 ----
+    lbank, lq, _ = cases.search_lattice_small()
+    idx = np.empty((len(lq), 10), dtype=np.int64)
+    sim = np.empty((len(lq), 10), dtype=np.float32)
+    for i, q in enumerate(lq):
+        idx[i], sim[i] = ref.top_k_cosine_similarity(q, lbank, 10)
+    out["search_lat_idx"], out["search_lat_sim"] = idx, sim
+
+    # ---- edge cases of vo:151-188 ----
+    eb, eq = cases.search_edge()
+    i1, s1 = ref.top_k_cosine_similarity(eq, eb, 4)
+    out["search_edge_idx"], out["search_edge_sim"] = i1, s1
+    i2, s2 = ref.top_k_cosine_similarity(eq, eb[:3], 8)        # k > N returns N
+    out["search_kgtn_idx"], out["search_kgtn_sim"] = i2, s2
+    i3, s3 = ref.top_k_cosine_similarity(eq, eb[5], 3)         # 1-D b
+    out["search_1d_idx"], out["search_1d_sim"] = i3, s3
+    out["cosine_pair"] = np.array([ref.cosine_similarity(eq, eb[5])], dtype=np.float64)
+
+    # ---- consolidation (hm:944-967) ----
+    for name, feats in cases.consolidation_cases().items():
+        for g in (0.9, 0.95):
+            out[f"cons_{name}_{int(g * 100)}"] = mem._select_key_frames(feats, None, g).astype(np.int64)
+    out["cons_default_gamma"] = mem._select_key_frames(cases.consolidation_cases()["c1"], None).astype(np.int64)
+
+    # ---- audio level (hm:993-1000) ----
+    pcm = cases.audio_case()
+    x = pcm.astype(np.float64) / 32768.0
+    wins = cases.audio_windows(len(pcm))
+    out["audio_levels"] = np.array([mem._compute_audio_level(x[s:s + n].reshape(-1, 1), 16000) for s, n in wins])
+    out["audio_level_stereo"] = np.array([mem._compute_audio_level(np.stack([x[:8000], x[8000:16000]], axis=1), 16000)])
+    out["audio_level_zero"] = np.array([mem._compute_audio_level(np.zeros(100), 16000)], dtype=np.float64)
+
+    # ---- frame difference (bp:32-71) ----
+    frames, _ = cases.frame_case()
+    pairs = cases.frame_diff_pairs()
+    out["frame_diff"] = np.array([ref.compute_frame_difference(frames[a], frames[b]) for a, b in pairs])
+    const = cases.constant_frames()
+    out["frame_diff_const"] = np.array([ref.compute_frame_difference(const[a], const[b]) for a, b in ((0, 0), (0, 1), (1, 2))])
+
+    # ---- frame similarity + segmentation through the reference's own code path (paths on disk) ----
+    import cv2
+
+    with tempfile.TemporaryDirectory() as td:
+        paths = []
+        for i, f in enumerate(frames):
+            p = os.path.join(td, f"f{i:05d}.png")          # PNG: lossless, so cv2.imread returns the same pixels
+            cv2.imwrite(p, f)
+            paths.append(p)
+        sims = np.array([mem._compute_frame_similarity(paths[i + 1], paths[i]) for i in range(len(paths) - 1)])
+        out["frame_ssim_adjacent"] = sims
+        cpaths = []
+        for i, f in enumerate(const):
+            p = os.path.join(td, f"c{i}.png")
+            cv2.imwrite(p, f)
+            cpaths.append(p)
+        with np.errstate(all="ignore"):
+            out["frame_ssim_const"] = np.array([mem._compute_frame_similarity(cpaths[a], cpaths[b])
+                                                for a, b in ((0, 1), (0, 2), (2, 0))])
+        times = cases.frame_times(len(frames))
+        audio = x[: int(times[-1] * 16000) + 16000].reshape(-1, 1)
+        for tag, kw in cases.segmentation_variants().items():
+            vf = paths if kw["video"] else None
+            ft = times if kw["video"] else None
+            au = audio if kw["audio"] else None
+            sr = 16000 if kw["audio"] else None
+            m2 = ref.make_memory(**kw["thresholds"])
+            segs = m2._segment_sequence(vf, ft, au, sr)
+            out[f"seg_{tag}"] = np.array([[s.start_time, s.end_time] for s in segs], dtype=np.float64).reshape(-1, 2)
+            out[f"seg_{tag}_nframes"] = np.array([len(s.frames) if s.frames is not None else -1 for s in segs])
+            out[f"seg_{tag}_nsamples"] = np.array([len(s.audio_data) if s.audio_data is not None else -1 for s in segs])
+
+    path = os.path.join(HERE, "reference_outputs.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")
+    for k, v in out.items():
+        print(f"  {k:28s} {v.dtype} {v.shape}")
+
+
+if __name__ == "__main__":
+    main()

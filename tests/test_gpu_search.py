@@ -1,0 +1,163 @@
+"""GPU parity: detailed-recall feature search (vo:151-188) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import hippo_oracle as O
+from parity import check_topk, check_topk_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def _search(bank, queries, k, path):
+    idx, score = bank.search(queries, k, path=path)
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), score.cpu().numpy()
+
+
+@pytest.mark.parametrize("path", ["single", "batched"])
+def test_config1_matches_reference_outputs(cuda_device, path):
+    """Config 1 (2,000 rows, 64 queries, k=5) against the unmodified reference's committed outputs."""
+    from hippomm_b200 import MemoryBank
+
+    bank_h, queries = cases.search_config1()
+    g = cases.golden()
+    bank = MemoryBank.from_rows(bank_h)
+    idx, score = _search(bank, queries, 5, path)
+    for qi in range(len(queries)):
+        check_topk(idx[qi], score[qi], g["search_c1_idx"][qi], g["search_c1_sim"][qi], what=f"{path} q{qi}")
+
+
+@pytest.mark.parametrize("path", ["single", "batched"])
+def test_lattice_is_bit_exact(cuda_device, path):
+    """On the bf16-exact lattice bank every fp32 partial sum is exact, so scores must equal the
+    reference's to the last bit and rows must match outright."""
+    from hippomm_b200 import MemoryBank
+
+    bank_h, queries, fam = cases.search_lattice_small()
+    g = cases.golden()
+    bank = MemoryBank.from_rows(bank_h)
+    assert bank.bf16_exact
+    idx, score = _search(bank, queries, 10, path)
+    for qi in range(len(queries)):
+        check_topk_exact(idx[qi], score[qi], g["search_lat_idx"][qi], g["search_lat_sim"][qi], what=f"{path} q{qi}")
+
+
+def test_wrapper_edge_cases(cuda_device):
+    """NaN rows first, ties, k > N, 1-D b, cosine_similarity: same contract as vo:151-188 / vo:6-20."""
+    from hippomm_b200 import cosine_similarity, top_k_cosine_similarity
+
+    b, q = cases.search_edge()
+    g = cases.golden()
+    i1, s1 = top_k_cosine_similarity(q, b, 4)
+    assert i1.dtype == np.int64 and s1.dtype == np.float32
+    assert i1[0] == 3 and np.isnan(s1[0])                     # zero-norm row: NaN sorts first
+    check_topk(i1, s1, g["search_edge_idx"], g["search_edge_sim"], what="edge")
+    assert i1[1] == 5 and abs(s1[1] - 1.0) < 1e-6
+    i2, s2 = top_k_cosine_similarity(q, b[:3], 8)             # k > N -> N results
+    check_topk(i2, s2, g["search_kgtn_idx"], g["search_kgtn_sim"], what="k>N")
+    i3, s3 = top_k_cosine_similarity(torch.from_numpy(q), torch.from_numpy(b[5]), 3)   # torch in, 1-D b
+    check_topk(i3, s3, g["search_1d_idx"], g["search_1d_sim"], what="1-D b")
+    assert abs(float(cosine_similarity(q, b[5])) - float(g["cosine_pair"][0])) < 1e-6
+    # ties: rows 2 and 9 are identical -> lower row first
+    i4, s4 = top_k_cosine_similarity(q, b, 16)
+    p2, p9 = list(i4).index(2), list(i4).index(9)
+    assert p9 == p2 + 1 and s4[p2] == s4[p9]
+    assert i4[-1] == 11 and abs(s4[-1] + 1.0) < 1e-6
+    # k == 0 keeps everything (argsort[-0:]), negative k drops the |k| smallest
+    i5, _ = top_k_cosine_similarity(q, b, 0)
+    assert len(i5) == 16
+    i6, _ = top_k_cosine_similarity(q, b, -14)
+    assert list(i6) == list(i4[:2])
+    # float64 bank (reloaded ThetaEvents, hm:391) keeps the reference's result dtype
+    i7, s7 = top_k_cosine_similarity(q, b.astype(np.float64), 4)
+    assert s7.dtype == np.float64 and list(i7) == list(i1)
+
+
+@pytest.mark.parametrize("path", ["single", "batched"])
+def test_paging_beyond_kmax(cuda_device, path):
+    """k above HIPPO_TOPK_MAX pages with the (score,row) cursor; must equal the full sort."""
+    from hippomm_b200 import MemoryBank
+
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((700, 128)).astype(np.float32)
+    q = rng.standard_normal((3, 128)).astype(np.float32)
+    bank = MemoryBank.from_rows(b)
+    idx, score = _search(bank, q, 100, path)
+    for qi in range(3):
+        ri, rs = O.top_k_cosine_similarity(q[qi], b, 100)
+        check_topk(idx[qi], score[qi], ri, rs, what=f"{path} paging q{qi}")
+    idx_all, score_all = _search(bank, q[:1], 700, path)
+    assert sorted(idx_all[0].tolist()) == list(range(700))
+    assert np.all(np.diff(score_all[0]) <= 0)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(1, 64, 1, 1), (5, 64, 2, 8), (255, 192, 130, 7), (257, 1024, 129, 32),
+                                      (1000, 320, 5, 10), (4099, 1024, 300, 10)])
+def test_ragged_shapes_both_paths_agree_with_oracle(cuda_device, n, d, nq, k):
+    """Row counts off the 256-row tile, query counts off the 128-row tile, d off 256: both kernels vs oracle."""
+    from hippomm_b200 import MemoryBank
+
+    rng = np.random.default_rng(n * 7 + d)
+    b = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    bank = MemoryBank.from_rows(b)
+    kk = min(k, n)
+    for path in ("single", "batched"):
+        idx, score = _search(bank, q, k, path)
+        for qi in range(0, nq, max(1, nq // 16)):
+            ri, rs = O.top_k_cosine_similarity(q[qi], b, k)
+            check_topk(idx[qi][:kk], score[qi][:kk], ri, rs, what=f"{path} n={n} d={d} q{qi}")
+            assert np.all(idx[qi][kk:] == -1)
+
+
+def test_lattice_1m_planted_families(cuda_device):
+    """1M-row lattice bank generated on the device: the top-10 of every query is its planted family
+    (members 0..9, spread over the whole bank), identical from both kernels, scores bit-equal to the
+    streaming oracle on a sample of queries."""
+    from hippomm_b200 import MemoryBank, synth
+
+    n, d, nq, seed = 1_000_000, 1024, 256, 4
+    bank = MemoryBank(n, d)
+    for r0 in range(0, n, 1 << 17):
+        m = min(1 << 17, n - r0)
+        bank.fill(r0, synth.lattice_rows_torch(seed, r0, m, d, n, cuda_device))
+    q, fam = synth.lattice_queries_np(seed, nq, d, n)
+    expect = synth.lattice_expected_topk(fam, n, 10)
+    bi, bs = _search(bank, q, 10, "batched")
+    assert np.array_equal(bi, expect)
+    si, ss = _search(bank, q[:8], 10, "single")
+    assert np.array_equal(si, expect[:8])
+    assert np.array_equal(ss.view(np.uint32), bs[:8].view(np.uint32))
+    # streaming CPU oracle over the candidate rows of 4 queries + a random slab (full 1M is the bench's job)
+    rows = np.unique(np.concatenate([expect[:4].reshape(-1), np.arange(5000, 9000)]))
+    sub = synth.lattice_rows_np(seed, rows, d, n)
+    for qi in range(4):
+        ri, rs = O.top_k_cosine_similarity(q[qi], sub, 10)
+        assert np.array_equal(rows[ri], bi[qi])
+        assert np.array_equal(rs.view(np.uint32), bs[qi].view(np.uint32))
+
+
+def test_row_base_and_merge(cuda_device, lib):
+    """Two half-banks with row offsets + hippo_topk_merge == one full bank (the sharded-search merge, §8e)."""
+    from hippomm_b200 import MemoryBank
+
+    bank_h, queries = cases.search_config1()
+    full = MemoryBank.from_rows(bank_h)
+    lo = MemoryBank.from_rows(bank_h[:1100])
+    hi = MemoryBank.from_rows(bank_h[1100:], row_base=1100)
+    fi, fs, fk = full.search_keys(queries, 5, "batched")
+    _, _, k0 = lo.search_keys(queries, 5, "batched")
+    _, _, k1 = hi.search_keys(queries, 5, "batched")
+    keys = torch.stack([k0, k1]).contiguous()
+    nq = len(queries)
+    oi = torch.empty((nq, 5), dtype=torch.int64, device=cuda_device)
+    os_ = torch.empty((nq, 5), dtype=torch.float32, device=cuda_device)
+    ok = torch.empty((nq, 5), dtype=torch.int64, device=cuda_device)
+    from hippomm_b200 import _cuda, _lib
+    _lib.check(lib.hippo_topk_merge(keys.data_ptr(), 2, nq, 5, 5, oi.data_ptr(), os_.data_ptr(), ok.data_ptr(),
+                                    _cuda.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(oi, fi) and torch.equal(ok, fk)
+    assert torch.equal(os_.view(torch.int32), fs.view(torch.int32))

@@ -1,0 +1,163 @@
+"""GPU parity: temporal pattern separation (hm:980-1114, bp:32-71) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import hippo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SSIM_TOL = 1e-6      # fp32 per-window ratio + fp64 mean vs the fp64 restatement
+DB_TOL = 1e-9        # fp64 on both sides; only log10's last ulp may differ
+
+
+def _ssim_adjacent(frames, dev, range_mode=0):
+    from hippomm_b200.segmentation import frame_pair_scores_device
+
+    fd = torch.from_numpy(frames).to(dev)
+    ssim, mse = frame_pair_scores_device(fd, range_mode=range_mode)
+    torch.cuda.synchronize()
+    return ssim.cpu().numpy(), mse.cpu().numpy()
+
+
+def test_frame_ssim_matches_reference_outputs(cuda_device):
+    frames, _ = cases.frame_case()
+    g = cases.golden()
+    ssim, _ = _ssim_adjacent(frames, cuda_device)
+    assert np.max(np.abs(ssim - g["frame_ssim_adjacent"])) < SSIM_TOL
+    # the decisions the state machine takes from them are identical
+    assert np.array_equal(ssim < 0.95, g["frame_ssim_adjacent"] < 0.95)
+
+
+@pytest.mark.parametrize("h,w", [(7, 7), (8, 300), (57, 63), (64, 64), (119, 257), (224, 224), (180, 320), (70, 600)])
+def test_frame_pairs_shapes_against_oracle(cuda_device, h, w):
+    """Frame sizes around the band (56 rows) and column-chunk (250 columns) boundaries; SSIM and MSE."""
+    from hippomm_b200 import synth
+
+    frames, _ = synth.frame_stream(h * 1000 + w, 6, h, w, min_scene=2, max_scene=3)
+    ssim, mse = _ssim_adjacent(frames, cuda_device)
+    ref = O.adjacent_ssim(frames)
+    assert np.max(np.abs(ssim - ref)) < SSIM_TOL
+    for p in range(len(frames) - 1):
+        g1 = O.bgr2gray(frames[p + 1]).astype(np.float64) / 255.0
+        g0 = O.bgr2gray(frames[p]).astype(np.float64) / 255.0
+        assert abs(mse[p] - np.mean((g1 - g0) ** 2)) < 1e-12
+    # gray (single channel) input takes the same path
+    gray = np.stack([O.bgr2gray(f) for f in frames])[..., None]
+    ssim_g, _ = _ssim_adjacent(np.ascontiguousarray(gray), cuda_device)
+    assert np.array_equal(ssim_g, ssim)
+
+
+def test_frame_similarity_and_difference_wrappers(cuda_device):
+    from hippomm_b200 import compute_frame_difference, compute_frame_similarity
+
+    frames, _ = cases.frame_case()
+    g = cases.golden()
+    for (a, b), want in zip(cases.frame_diff_pairs(), g["frame_diff"]):
+        assert abs(compute_frame_difference(frames[a], frames[b]) - want) < SSIM_TOL
+    const = cases.constant_frames()
+    for (a, b), want in zip(((0, 0), (0, 1), (1, 2)), g["frame_diff_const"]):
+        assert abs(compute_frame_difference(const[a], const[b]) - want) < SSIM_TOL
+    # constant first frame: data range 0 -> 0/0 -> NaN exactly where the reference gives NaN (hm:990)
+    for (a, b), want in zip(((0, 1), (0, 2), (2, 0)), g["frame_ssim_const"]):
+        got = compute_frame_similarity(const[a], const[b])
+        assert (np.isnan(got) and np.isnan(want)) or abs(got - want) < SSIM_TOL
+    assert abs(compute_frame_similarity(frames[31], frames[30]) - g["frame_ssim_adjacent"][30]) < SSIM_TOL
+    tiny = np.zeros((5, 5, 3), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        compute_frame_similarity(tiny, tiny)                    # skimage raises for images below 7x7
+    assert compute_frame_difference(tiny, tiny + 255) == 1.0     # bp:64-71: exception -> MSE fallback
+
+
+def test_audio_levels_match_reference_outputs(cuda_device):
+    from hippomm_b200 import compute_audio_level
+    from hippomm_b200.segmentation import audio_energy_device, audio_levels_device
+
+    pcm = cases.audio_case()
+    g = cases.golden()
+    wins = cases.audio_windows(len(pcm))
+    ws = torch.tensor([w[0] for w in wins], dtype=torch.int64)
+    wl = torch.tensor([w[1] for w in wins], dtype=torch.int64)
+    x64 = pcm.astype(np.float64) / 32768.0
+    for name, arr in (("i16", pcm), ("f32", x64.astype(np.float32)), ("f64", x64)):
+        t = torch.from_numpy(arr).to(cuda_device).reshape(-1, 1)
+        pyr = audio_energy_device(t)
+        direct = audio_levels_device(t, ws, wl).cpu().numpy()
+        viapyr = audio_levels_device(t, ws, wl, pyramid=pyr).cpu().numpy()
+        assert np.max(np.abs(direct - g["audio_levels"])) < DB_TOL, name
+        assert np.max(np.abs(viapyr - g["audio_levels"])) < DB_TOL, name
+        # int16-origin PCM: all sums of squares are exact in fp64, whatever the order
+        e16, e512 = pyr
+        ref16 = np.add.reduceat(x64 * x64, np.arange(0, len(x64), 16))
+        assert np.array_equal(e16.cpu().numpy(), ref16), name
+        assert np.array_equal(e512.cpu().numpy(), np.add.reduceat(x64 * x64, np.arange(0, len(x64), 512))), name
+    stereo = np.stack([x64[:8000], x64[8000:16000]], axis=1)
+    assert abs(compute_audio_level(stereo, 16000) - g["audio_level_stereo"][0]) < DB_TOL
+    assert compute_audio_level(np.zeros(100), 16000) == -100
+    assert compute_audio_level(x64[:8000].reshape(-1, 1), 16000) == pytest.approx(g["audio_levels"][0], abs=DB_TOL)
+    # ragged length, stereo, through the generic pyramid kernel
+    st = torch.from_numpy(np.ascontiguousarray(np.stack([x64[:100003], x64[7:100010]], axis=1))).to(cuda_device)
+    pyr = audio_energy_device(st)
+    lv = audio_levels_device(st, torch.tensor([5, 90000]), torch.tensor([8000, 20000]), pyramid=pyr).cpu().numpy()
+    mono = st.cpu().numpy().mean(axis=1)
+    assert abs(lv[0] - O.compute_audio_level(mono[5:8005])) < DB_TOL
+    assert abs(lv[1] - O.compute_audio_level(mono[90000:100003])) < DB_TOL      # window clipped like a NumPy slice
+
+
+@pytest.mark.parametrize("tag", ["av", "a", "v", "av_short", "v_short"])
+def test_segment_sequence_matches_reference_outputs(cuda_device, tag):
+    """Boundaries equal to the unmodified reference's (exact fp64), plus the frames / samples per segment."""
+    from hippomm_b200 import segment_sequence
+
+    frames, _ = cases.frame_case()
+    g = cases.golden()
+    kw = cases.segmentation_variants()[tag]
+    times = cases.frame_times(len(frames))
+    pcm = cases.audio_case()
+    x = pcm.astype(np.float64) / 32768.0
+    audio = x[: int(times[-1] * 16000) + 16000].reshape(-1, 1)
+    segs = segment_sequence(frames if kw["video"] else None, times if kw["video"] else None,
+                            audio if kw["audio"] else None, 16000 if kw["audio"] else None, **kw["thresholds"])
+    got = np.array([[s.start_time, s.end_time] for s in segs]).reshape(-1, 2)
+    assert np.array_equal(got, g[f"seg_{tag}"]), f"{got} vs {g[f'seg_{tag}']}"
+    nfr = [len(s.frames) if s.frames is not None else -1 for s in segs]
+    nsm = [len(s.audio_data) if s.audio_data is not None else -1 for s in segs]
+    assert nfr == g[f"seg_{tag}_nframes"].tolist()
+    assert nsm == g[f"seg_{tag}_nsamples"].tolist()
+
+
+def test_segment_edge_cases(cuda_device):
+    from hippomm_b200 import segment_sequence
+
+    assert segment_sequence() == []
+    assert segment_sequence(None, None, np.zeros(0), 16000) == []
+    # audio shorter than the video: windows past the end are empty -> -100 dB -> "silent" (NumPy slice clipping)
+    frames, _ = cases.frame_case()
+    times = cases.frame_times(60)
+    x = cases.audio_case()[: 20 * 16000].astype(np.float64) / 32768.0
+    segs = segment_sequence(frames[:60], times, x.reshape(-1, 1), 16000)
+    ss = O.adjacent_ssim(frames[:60])
+    want = O.segment_boundaries(ss, times, x.reshape(-1, 1), 16000)
+    assert [(s.start_time, s.end_time) for s in segs] == want
+    # int16 input on the device side gives the same boundaries as the float64 the reference sees
+    segs16 = segment_sequence(None, None, cases.audio_case()[: 120 * 16000], 16000)
+    x120 = cases.audio_case()[: 120 * 16000].astype(np.float64) / 32768.0
+    want = O.segment_boundaries(None, None, x120, 16000)
+    assert [(s.start_time, s.end_time) for s in segs16] == want
+
+
+def test_one_hour_stream_against_oracle(cuda_device):
+    """Config 2 geometry at reduced resolution: 3,600 frames + 57.6M int16 samples; boundaries must equal
+    the oracle's exactly (the oracle needs ~20 s for the SSIM restatement at 64x64)."""
+    from hippomm_b200 import segment_sequence, synth
+
+    frames, _ = synth.frame_stream(21, 3600, 64, 64)
+    pcm = synth.audio_stream_int16(22, 3600 * 16000)
+    times = cases.frame_times(3600)
+    segs = segment_sequence(frames, times, pcm.reshape(-1, 1), 16000)
+    ss = O.adjacent_ssim(frames)
+    x = pcm.astype(np.float64) / 32768.0
+    want = O.segment_boundaries(ss, times, x.reshape(-1, 1), 16000)
+    assert [(s.start_time, s.end_time) for s in segs] == want
+    assert 100 <= len(segs) <= 400
