@@ -6,15 +6,23 @@ import torch
 
 from . import _cuda, _lib
 
-# similarity bands inside which a tensor-core (bf16-input) similarity is not trusted and the pair
-# is re-evaluated from the fp32 rows: rows that are exactly bf16-representable only suffer fp32
-# accumulation-order noise; otherwise the bf16 rounding of the inputs dominates.
+# Similarity bands inside which a tensor-core (bf16-input) similarity is not trusted and the pair
+# is re-evaluated from the fp32 rows.  Both are rigorous bounds, so a decision outside the band can
+# never differ from the fp64 evaluation:
+#   * rows that are exactly bf16-representable only suffer fp32 accumulation error,
+#     <= d * 2^-24 * sum|a_i b_i| / (|a||b|) <= d * 6e-8  (6.1e-5 at d = 1024);
+#   * otherwise each operand carries a relative rounding error <= 2^-8, so
+#     |sim_bf16 - sim| <= (2 * 2^-8 + 2^-16) * sum|a_i b_i| / (|a||b|) <= 7.83e-3 (Cauchy-Schwarz).
 BAND_EXACT = 1e-4
-BAND_INEXACT = 4e-3
+BAND_INEXACT = 7.9e-3
+
+
+def _band_exact(d: int) -> float:
+    return max(BAND_EXACT, d * 1.2e-7)
 
 
 def select_key_frames_device(features: torch.Tensor, similarity_threshold: float = 0.9,
-                             band_exact: float = BAND_EXACT, band_inexact: float = BAND_INEXACT):
+                             band_exact: float | None = None, band_inexact: float = BAND_INEXACT):
     """Greedy redundancy filter on a device tensor (n, d) fp32, d % 64 == 0.
 
     Returns (kept int64 [n] device tensor, count int32 [1] device tensor, stats int32 [4] device tensor);
@@ -27,6 +35,8 @@ def select_key_frames_device(features: torch.Tensor, similarity_threshold: float
     n, d = features.shape
     if d % 64:
         raise ValueError("d must be a multiple of 64 (pad with zero columns)")
+    if band_exact is None:
+        band_exact = _band_exact(d)
     kept = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
     count = torch.zeros((1,), dtype=torch.int32, device=dev)
     stats = torch.zeros((4,), dtype=torch.int32, device=dev)

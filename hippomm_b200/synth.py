@@ -7,14 +7,16 @@ the oracle regenerates exactly the rows it needs on the host.
 Lattice bank ("bf16-exact"):  value = k / 128 with integer |k| <= 127.
   * row r belongs to family f = r % F (F families) and is member m = r // F of it;
   * k(r, c) = base(f, c) + noise(r, c), base uniform in [-64, 64], noise uniform in [-L_m, L_m]
-    with L_m = 6 * min(m, 10): member 0 is the family centre, members 1..9 are graded copies
-    (cosine to the centre about .995, .98, .96, .93, .90, .87, .83, .80, .76), members >= 10
-    share the coarsest level;
+    with L_m = 3 m for m <= 9 and L_m = 63 for m >= 10: member 0 is the family centre, members
+    1..9 are graded copies (expected cosine to a query of the family about .997, .994, .988,
+    .980, .971, .960, .948, .934, .919), members >= 10 are far copies (about .71);
   * a query for family f is the centre plus uniform noise in [-3, 3].
 Every product of two lattice values is a multiple of 2^-14 and every dot product / squared
 norm stays below 2^24 such units, so fp32 accumulation is exact in ANY order: the reference's
-NumPy scores, the GEMV kernel and the tensor-core kernel agree to the last bit, and the true
-top-10 of a query (its family) is separated by gaps of 1e-2, far above the 1e-3 tolerance.
+NumPy scores, the GEMV kernel and the tensor-core kernel agree to the last bit.  The true
+top-10 of a query is its family's members 0..9 as a SET (8 sigma clear of member 10 and of
+unrelated rows, which score about 0 +- .03); the order inside the set follows the grading
+only on average.
 """
 from __future__ import annotations
 
@@ -26,8 +28,9 @@ except Exception:  # pragma: no cover
     torch = None
 
 _M32 = 0xFFFFFFFF
-_LEVEL_STEP = 6
-_LEVEL_CAP = 10
+_LEVEL_STEP = 3
+_NEAR_MEMBERS = 10
+_FAR_AMP = 63
 _BASE_AMP = 64
 _QUERY_AMP = 3
 
@@ -89,7 +92,7 @@ def lattice_rows_np(seed: int, rows: np.ndarray, d: int, n_total: int) -> np.nda
     mem = rows // F
     cols = np.arange(d, dtype=np.int64)[None, :]
     base = _uniform_int_np(_hash_np(seed, fam[:, None] * d + cols), _BASE_AMP)
-    lvl = (_LEVEL_STEP * np.minimum(mem, _LEVEL_CAP))[:, None]
+    lvl = np.where(mem < _NEAR_MEMBERS, _LEVEL_STEP * mem, _FAR_AMP)[:, None]
     noise = _uniform_int_np(_hash_np(seed + 1, rows[:, None] * d + cols), lvl)
     return ((base + noise).astype(np.float32)) / np.float32(128.0)
 
@@ -106,7 +109,8 @@ def lattice_queries_np(seed: int, n_queries: int, d: int, n_total: int) -> tuple
 
 
 def lattice_expected_topk(fam: np.ndarray, n_total: int, k: int) -> np.ndarray:
-    """Rows of the k least-noisy members of each query's family (valid for k <= 10 and n_total >= 16*k)."""
+    """Rows of members 0..k-1 of each query's family: for k = 10 (and n_total >= 160) exactly the SET of
+    the query's top-10 rows; the order inside the set is only graded on average."""
     F = lattice_families(n_total)
     return fam[:, None] + F * np.arange(k, dtype=np.int64)[None, :]
 
@@ -120,7 +124,7 @@ def lattice_rows_torch(seed: int, row0: int, n_rows: int, d: int, n_total: int, 
     cols = torch.arange(d, dtype=torch.int64, device=device)[None, :]
     hb = _hash_t(seed, fam[:, None] * d + cols)
     base = hb % (2 * _BASE_AMP + 1) - _BASE_AMP
-    lvl = (_LEVEL_STEP * torch.clamp(mem, max=_LEVEL_CAP))[:, None]
+    lvl = torch.where(mem < _NEAR_MEMBERS, _LEVEL_STEP * mem, torch.full_like(mem, _FAR_AMP))[:, None]
     hn = _hash_t(seed + 1, rows[:, None] * d + cols)
     noise = hn % (2 * lvl + 1) - lvl
     vals = (base + noise).to(torch.float32) / 128.0

@@ -126,9 +126,9 @@ def test_lattice_1m_planted_families(cuda_device):
     q, fam = synth.lattice_queries_np(seed, nq, d, n)
     expect = synth.lattice_expected_topk(fam, n, 10)
     bi, bs = _search(bank, q, 10, "batched")
-    assert np.array_equal(bi, expect)
+    assert np.array_equal(np.sort(bi, axis=1), expect)
     si, ss = _search(bank, q[:8], 10, "single")
-    assert np.array_equal(si, expect[:8])
+    assert np.array_equal(si, bi[:8])
     assert np.array_equal(ss.view(np.uint32), bs[:8].view(np.uint32))
     # streaming CPU oracle over the candidate rows of 4 queries + a random slab (full 1M is the bench's job)
     rows = np.unique(np.concatenate([expect[:4].reshape(-1), np.arange(5000, 9000)]))
