@@ -243,7 +243,10 @@ def run_gpu_arm(args):
     import __graft_entry__ as entry
 
     if rank == 0:
-        entry.build()
+        import contextlib
+
+        with contextlib.redirect_stdout(sys.stderr):   # stdout carries the JSON line only
+            entry.build()
     barrier()
     from hippomm_b200 import MemoryBank, _cuda, _lib, synth
     from hippomm_b200.distributed import gather_keys, merge_keys, shard_range

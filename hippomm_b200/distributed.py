@@ -29,7 +29,11 @@ def gather_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather of the local order keys [nq, k] (int64 bit patterns) -> [world, nq, k] on every rank."""
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    try:
+        dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):
+        # backends without the flat variant (some gloo builds, used by the CPU tests)
+        dist.all_gather(list(out.unbind(0)), keys.contiguous(), group=group)
     return out
 
 

@@ -1,0 +1,132 @@
+"""CPU: host-side logic of the drop-in layer (no kernels run here)."""
+import numpy as np
+import pytest
+import torch
+
+import hostref
+from hippomm_b200 import synth
+from hippomm_b200.distributed import shard_range
+from oracle import hippo_oracle as O
+
+needs_no_gpu = pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a CUDA device")
+
+
+def test_synth_numpy_and_torch_generators_agree():
+    for n_total, r0, m, d in ((10_000, 100, 64, 256), (1_000_000, 999_900, 100, 128), (80_000_000, 79_999_990, 10, 64)):
+        a = synth.lattice_rows_np(4, np.arange(r0, r0 + m), d, n_total)
+        b = synth.lattice_rows_torch(4, r0, m, d, n_total, "cpu").numpy()
+        assert np.array_equal(a, b)
+        assert np.abs(a * 128).max() <= 127 and np.array_equal(a * 128, np.rint(a * 128))
+        assert np.array_equal(synth.round_to_bf16(a), a)              # bf16-exact
+    q, fam = synth.lattice_queries_np(4, 16, 64, 10_000)
+    assert q.shape == (16, 64) and fam.max() < synth.lattice_families(10_000)
+    assert np.array_equal(synth.round_to_bf16(q), q)
+
+
+def test_lattice_dot_products_are_order_independent_in_fp32():
+    """The property the bit-exact parity rests on: every partial sum is an integer below 2^24 (units 2^-14)."""
+    rows = synth.lattice_rows_np(4, np.arange(0, 4000, 7), 1024, 8192)
+    q, _ = synth.lattice_queries_np(4, 4, 1024, 8192)
+    ints_r = np.rint(rows * 128).astype(np.int64)
+    ints_q = np.rint(q * 128).astype(np.int64)
+    assert (np.abs(ints_r) @ np.abs(ints_q).T).max() < 2 ** 24
+    exact = (ints_r @ ints_q.T).astype(np.float64) / 2 ** 14
+    assert np.array_equal(np.dot(rows, q.T).astype(np.float64), exact)
+    perm = np.random.default_rng(0).permutation(1024)
+    assert np.array_equal(np.dot(rows[:, perm], q[:, perm].T).astype(np.float64), exact)
+
+
+def test_round_to_bf16_matches_torch():
+    x = np.random.default_rng(1).standard_normal(10_000).astype(np.float32) * 37.0
+    assert np.array_equal(synth.round_to_bf16(x), torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy())
+
+
+def test_order_keys_sort_like_the_canonical_rule():
+    rng = np.random.default_rng(2)
+    s = rng.standard_normal(300).astype(np.float32)
+    s[[5, 77]] = np.nan
+    s[[10, 11, 12]] = s[10]
+    s[200] = np.inf
+    s[201] = -np.inf
+    s[202], s[203] = 0.0, -0.0
+    keys = hostref.pack_keys(s, np.arange(300))
+    order = np.argsort(keys)[::-1]
+    ci, _ = O.canonical_topk(s, 300)
+    # -0.0 < +0.0 in key order while they compare equal as floats; every other position must agree
+    mism = np.nonzero(order != ci)[0]
+    assert set(order[mism].tolist()) <= {202, 203}
+    assert order[0] == 5 and order[1] == 77 and order[2] == 200 and order[-1] == 201
+    assert np.array_equal(hostref.key_rows(keys), np.arange(300))
+    assert keys.min() > 0                                               # 0 is reserved for "empty slot"
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (7, 8), (10_000_000, 8), (80_000_000, 8), (0, 4)])
+def test_shard_ranges_partition_the_bank(n, world):
+    edges = [shard_range(n, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in edges]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(n, world, world)
+
+
+def test_trivial_inputs_never_touch_the_device():
+    import hippomm_b200 as hb
+
+    idx, sims = hb.top_k_cosine_similarity(np.ones(64, np.float32), np.zeros((0, 64), np.float32), 3)
+    assert idx.shape == (0,) and idx.dtype == np.int64 and sims.shape == (0,)
+    assert np.array_equal(hb.select_key_frames(np.ones((2, 8), np.float32), None), np.arange(2))   # hm:946-947
+    assert np.array_equal(hb.select_key_frames(np.ones((0, 8), np.float32), None), np.arange(0))
+    assert hb.segment_sequence() == []                                                          # hm:1024-1025
+    assert hb.segment_sequence(None, None, np.zeros(0), 16000) == []
+    assert hb.segment_sequence(["a"], [], None, None) == []
+    with pytest.raises(ValueError):
+        hb.segment_sequence(None, None, np.zeros(16000), 16000, min_segment_duration=0.0)
+
+
+@needs_no_gpu
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point raises; nothing is silently computed on the host."""
+    import hippomm_b200 as hb
+
+    b = np.random.default_rng(0).standard_normal((10, 64)).astype(np.float32)
+    for call in (
+        lambda: hb.top_k_cosine_similarity(b[0], b, 3),
+        lambda: hb.cosine_similarity(b[0], b[1]),
+        lambda: hb.select_key_frames(b, None),
+        lambda: hb.compute_audio_level(np.zeros(100), 16000),
+        lambda: hb.compute_frame_difference(np.zeros((8, 8, 3), np.uint8), np.zeros((8, 8, 3), np.uint8)),
+        lambda: hb.segment_sequence(None, None, np.ones(32000), 16000),
+        lambda: hb.MemoryBank.from_rows(b),
+    ):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_install_rebinds_the_reference_symbols():
+    from oracle import reference_shim
+
+    if not reference_shim.available():
+        pytest.skip("reference checkout not present")
+    import hippomm_b200 as hb
+
+    ref = reference_shim.load()          # registers the stubs and puts the reference on sys.path
+    vo, hm, bp = ref.modules
+    orig = (vo.top_k_cosine_similarity, hm.top_k_cosine_similarity, hm.HippocampalMemory._select_key_frames,
+            hm.HippocampalMemory._segment_sequence, bp.compute_frame_difference)
+    hb.install()
+    try:
+        assert vo.top_k_cosine_similarity is hb.top_k_cosine_similarity
+        assert hm.top_k_cosine_similarity is hb.top_k_cosine_similarity       # the from-import copy (hm:28)
+        assert hm.HippocampalMemory._select_key_frames is not orig[2]
+        assert hm.HippocampalMemory._segment_sequence is not orig[3]
+        assert bp.compute_frame_difference is hb.compute_frame_difference
+        m = ref.make_memory()
+        assert np.array_equal(m._select_key_frames(np.ones((2, 4), np.float32), None), np.arange(2))
+        assert m._segment_sequence() == []
+    finally:
+        hb.uninstall()
+    assert (vo.top_k_cosine_similarity, hm.top_k_cosine_similarity, hm.HippocampalMemory._select_key_frames,
+            hm.HippocampalMemory._segment_sequence, bp.compute_frame_difference) == orig
