@@ -3,33 +3,45 @@
 //
 //   EPI_TOPK : batched detailed-recall search.  A = queries, B = bank rows.  Reference:
 //              nq sequential top_k_cosine_similarity calls (vo:151-188, callers hm:3153,3304).
-//              Each epilogue thread owns one query (one TMEM lane), scales the 256 dots of a
-//              tile by 1/|b|, and only values passing a running k-th-best threshold reach
-//              the exact IEEE evaluation dot/(|b||a|) and the thread's sorted top-k list.
+//              An epilogue thread owns one query row x 128 bank columns of a tile, scales the dots
+//              by 1/|b| and only values passing a running k-th-best threshold reach the exact
+//              IEEE evaluation dot/(|b||a|) and the thread's sorted top-k list.
 //   EPI_MASK : memory consolidation.  A = B = feature rows.  Reference: the N x N
 //              `np.dot(Fn, Fn.T)` of hm:952 and the `< threshold` test of hm:960.  Only the
 //              lower triangle is contracted; the epilogue emits 1 bit per pair plus the
 //              list of pairs too close to gamma to trust bf16 inputs.
 //
-// Structure (one CTA per SM, persistent): warp 0 = TMA producer (128B-swizzled K-major
-// tiles, 4-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (M128 N256 K16,
-// fp32 accumulators double-buffered across the 512 TMEM columns), warps 2..5 = epilogue
-// (tcgen05.ld 32x32b, one TMEM lane quarter per warp).
+// Structure (persistent, one CTA per SM, CTAs paired into 2-CTA clusters): the pair computes a
+// 256 x 256 tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of
+// the B tile (128 rows), the tensor core of each SM reads the other half from the peer's shared
+// memory, and each CTA's TMEM receives its 128 rows of the result.
+//   warp 0     TMA producer (128B-swizzled K-major tiles, 6-stage mbarrier ring).  Only the pair
+//              LEADER arrives on a stage's full barrier (arrive.expect_tx for the bytes of both CTAs);
+//              the peer's TMA credits its bytes to the leader's barrier directly, so no cross-CTA
+//              arrive sits on the per-stage critical path (that alone was worth 2x, profiles/).
+//   warp 1     MMA issuer (leader CTA only, one thread; M256 N256 K16; fp32 accumulators double-
+//              buffered across the 512 TMEM columns; tcgen05.commit multicast to both CTAs).
+//   warps 2-9  epilogue: two warps per TMEM lane quarter, each taking 128 of the tile's 256 columns
+//              (tcgen05.ld 32x32b), next tile's column norms / thresholds prefetched under the math.
 #include "sim_tc.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace hippo {
 
 constexpr int EPI_TOPK = 0;
 constexpr int EPI_MASK = 1;
 
-constexpr uint32_t kABytes = kTcBM * kTcBK * 2;           // 16 KiB
-constexpr uint32_t kBBytes = kTcBN * kTcBK * 2;           // 32 KiB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;       // 48 KiB
+constexpr uint32_t kABytes = kTcBM * kTcBK * 2;           // 16 KiB: this CTA's 128 rows of A
+constexpr uint32_t kBBytes = (kTcBN / 2) * kTcBK * 2;     // 16 KiB: this CTA's half of the B tile
+constexpr uint32_t kStageBytes = kABytes + kBBytes;       // 32 KiB per CTA and stage
 constexpr uint32_t kTmemCols = 512;                       // 2 accumulators x 256 columns
+constexpr int kEpiThreads = kTcThreads - 64;              // 256
+constexpr int kEpiWarps = kEpiThreads / 32;               // 8
 constexpr size_t kSmemTiles = (size_t)kTcStages * kStageBytes;
-constexpr size_t kSmemCols = 2 * 2 * kTcBN * sizeof(float);  // [buf][norm|inv][256]
+constexpr size_t kSmemColF = 2 * 2 * kTcBN * sizeof(float);           // [buf][norm|inv][256]
+constexpr size_t kSmemCols = kSmemColF + 2 * 8 * sizeof(uint32_t);    // + [buf][8] special-column masks
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kSmemTiles + kSmemCols + 256 /*barriers*/;
 
 struct TcParams {
@@ -38,13 +50,15 @@ struct TcParams {
   int kblocks;        // d / 64
   const float* bnorm; // norms of B rows
   int units;
+  int debug;          // profiling knobs (HIPPO_TC_DEBUG): 1 = no epilogue math, 16 = no TMA loads, 32 = no MMAs
   // top-k
   const float* qnorm;
-  int nq, k, m_blocks, n_tiles, splits, tiles_per_split;
+  int nq, k, m_pairs /* 256-query blocks */, n_tiles, splits, tiles_per_split;
   int64_t row_base;
   const uint64_t* after_key;
-  uint64_t* part;
-  uint32_t* thr_ord;
+  uint64_t* part;     // [2 * splits, nq, k]
+  uint32_t* thr_ord;  // [nq]      global lower bound on the k-th best score (monotone, atomicMax)
+  uint32_t* pool;     // [nq, k]   global pool of the best scores seen by anyone (see pool_insert)
   // mask
   float gamma, band_exact, band_inexact;
   const int32_t* inexact;
@@ -55,29 +69,52 @@ struct TcParams {
   int32_t uncertain_cap;
 };
 
-// A unit is what one CTA takes from the static schedule: `m_count` row blocks starting at
-// `m_first`, each against bank tiles [t0, t1).
+// One tile of a pair's static schedule.  A unit is (256-row block, range of bank tiles); the row block
+// varies fastest across pairs so the pairs running concurrently stream the same bank tiles through L2.
+struct Tile {
+  int unit, m_base, t, t1, split;
+  bool first;   // first tile of its unit
+};
+
 template <int EPI>
-__device__ __forceinline__ void decode_unit(const TcParams& p, int unit, int& m_first, int& m_count,
-                                            int& t0, int& t1, int& split) {
+__device__ __forceinline__ void decode_unit(const TcParams& p, int unit, int& m_base, int& t0, int& t1,
+                                            int& split) {
   if constexpr (EPI == EPI_TOPK) {
-    // query block varies fastest so the CTAs running concurrently share bank tiles in L2
-    split = unit / p.m_blocks;
-    m_first = unit - split * p.m_blocks;
-    m_count = 1;
+    split = unit / p.m_pairs;
+    m_base = 2 * (unit - split * p.m_pairs);
     t0 = split * p.tiles_per_split;
     t1 = min(t0 + p.tiles_per_split, p.n_tiles);
   } else {
-    // lower triangle of 256 x 256 super-blocks: unit = I(I+1)/2 + t, t <= I
+    // lower triangle of 256 x 256 blocks: unit = I(I+1)/2 + t, t <= I
     int I = (int)((sqrtf(8.f * (float)unit + 1.f) - 1.f) * 0.5f);
     while ((int64_t)(I + 1) * (I + 2) / 2 <= unit) ++I;
     while ((int64_t)I * (I + 1) / 2 > unit) --I;
     t0 = unit - (int)((int64_t)I * (I + 1) / 2);
     t1 = t0 + 1;
-    m_first = 2 * I;
-    m_count = ((int64_t)(2 * I + 1) * kTcBM < p.n) ? 2 : 1;
+    m_base = 2 * I;
     split = 0;
   }
+}
+template <int EPI>
+__device__ __forceinline__ bool first_tile(const TcParams& p, int pair, Tile& x) {
+  if (pair >= p.units) return false;
+  int t0;
+  x.unit = pair;
+  decode_unit<EPI>(p, x.unit, x.m_base, t0, x.t1, x.split);
+  x.t = t0;
+  x.first = true;
+  return true;
+}
+template <int EPI>
+__device__ __forceinline__ bool next_tile(const TcParams& p, int npairs, Tile& x) {
+  if (x.t + 1 < x.t1) { ++x.t; x.first = false; return true; }
+  if (x.unit + npairs >= p.units) return false;
+  int t0;
+  x.unit += npairs;
+  decode_unit<EPI>(p, x.unit, x.m_base, t0, x.t1, x.split);
+  x.t = t0;
+  x.first = true;
+  return true;
 }
 
 __device__ __forceinline__ float topk_filter_threshold(uint64_t kth_key, float an) {
@@ -86,51 +123,114 @@ __device__ __forceinline__ float topk_filter_threshold(uint64_t kth_key, float a
   if (ord == 0xffffffffu) return INFINITY;
   float lo = ord_to_score(ord) * an;
   if (isinf(lo)) return lo;
-  return lo - fabsf(lo) * 9.5367431640625e-07f - 1e-37f;
+  return lo - fabsf(lo) * 9.5367431640625e-07f - 1e-37f;   // 2^-20 relative slack
+}
+
+// Global per-query pool of the k best score-ords any thread has inserted so far.  Insertion bubbles the
+// value down the k slots with atomicMax (slot keeps the larger, the smaller is carried on), which preserves
+// the multiset {pool} U {carried} at every step under any interleaving; every slot therefore always holds
+// the score of a DISTINCT eligible row, and min(pool) is a valid lower bound on the final k-th best score.
+// It is published through thr_ord (atomicMax), which only gates the approximate filter (with slack): results
+// do not depend on timing.
+__device__ __forceinline__ void pool_insert(uint32_t* pool_q, int k, uint32_t ord, uint32_t* thr_ord_q) {
+  uint32_t v = ord;
+  for (int j = 0; j < k && v != 0; ++j) {
+    const uint32_t old = atomicMax(&pool_q[j], v);
+    v = old < v ? old : v;
+  }
+  uint32_t m = 0xffffffffu;
+  for (int j = 0; j < k; ++j) {
+    const uint32_t g = __ldcg(&pool_q[j]);
+    m = g < m ? g : m;
+  }
+  if (m != 0) atomicMax(thr_ord_q, m);
 }
 
 // Exact evaluation + list insertion of one candidate (rare path, kept out of line).
 __device__ __noinline__ void topk_consider(uint64_t* list, int k, float dot, float bn, float an,
-                                           uint32_t grow, uint64_t below, uint32_t* thr_ord_q) {
+                                           uint32_t grow, uint64_t below, uint32_t* thr_ord_q,
+                                           uint32_t* pool_q) {
   // the reference's operation order (vo:182): dot / (|b| * |a|), IEEE fp32
   float s = __fdiv_rn(dot, __fmul_rn(bn, an));
   uint64_t key = pack_key(s, grow);
   if (key < below && key > list[k - 1]) {
     topk_insert(list, k, key);
-    if (list[k - 1] != 0) atomicMax(thr_ord_q, (uint32_t)(list[k - 1] >> 32));
+    const uint32_t ord = (uint32_t)(key >> 32);
+    if (ord > __ldcg(thr_ord_q)) pool_insert(pool_q, k, ord, thr_ord_q);
   }
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Rare path of the search epilogue: one 32-column chunk of one query row whose quick test fired.
+// `acc` is the thread's copy of the 32 accumulators (local memory); returns the updated filter threshold.
+__device__ __noinline__ float topk_slow_chunk(const float* acc, const float* inv, const float* bn, int64_t col0,
+                                              int64_t n, uint64_t* list, int k, float an, int64_t row_base,
+                                              uint64_t below, uint32_t* thr_ord_q, uint32_t* pool_q, float thr,
+                                              bool force) {
+  for (int j = 0; j < 32; ++j) {
+    const float dot = acc[j];
+    const float tv = dot * inv[j];
+    if (force || !(tv < thr)) {                          // NaN passes, as np.argsort ranks NaN first (vo:185)
+      const int64_t col = col0 + j;
+      if (col < n) {
+        topk_consider(list, k, dot, bn[j], an, (uint32_t)(row_base + col), below, thr_ord_q, pool_q);
+        uint64_t kth = list[k - 1];
+        const uint64_t g = (uint64_t)__ldcg(thr_ord_q) << 32;
+        kth = g > kth ? g : kth;
+        thr = topk_filter_threshold(kth, an);
+      }
+    }
+  }
+  return thr;
+}
+
+// Rare path of the consolidation epilogue: append the pairs of this chunk that sit inside the band.
+__device__ __noinline__ void mask_uncertain_chunk(const float* acc, const float* inv, float g_i, float b_i,
+                                                  uint32_t keep, uint32_t arow, uint32_t jb, uint2* uncertain,
+                                                  int32_t* count, int32_t cap) {
+  for (int j = 0; j < 32; ++j) {
+    const float d = fmaf(acc[j], inv[j], -g_i);
+    if ((fabsf(d) <= b_i) && ((keep >> j) & 1u)) {
+      const int pos = atomicAdd(count, 1);
+      if (pos < cap) uncertain[pos] = make_uint2(arow, jb + j);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_cols = reinterpret_cast<float*>(smem + kSmemTiles);      // [buf][2][256]
+  // identical carve-up in both CTAs of the pair: the MMA and the multicast commits address the peer's
+  // shared memory by the same offsets (pointer arithmetic on the __shared__ array keeps LDS/STS)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* s_cols = reinterpret_cast<float*>(smem + kSmemTiles);                     // [buf][2][256]
+  uint32_t* s_spec = reinterpret_cast<uint32_t*>(smem + kSmemTiles + kSmemColF);   // [buf][8]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles + kSmemCols);
-  uint64_t* full = bars;                 // [stages]  TMA -> MMA
-  uint64_t* empty = bars + kTcStages;    // [stages]  MMA -> TMA
-  uint64_t* tfull = bars + 2 * kTcStages;      // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 2 * kTcStages + 2; // [2] epilogue -> MMA
+  uint64_t* full = bars;                       // [stages] TMA (both CTAs) -> MMA; the leader's copy is used
+  uint64_t* empty = bars + kTcStages;          // [stages] MMA -> TMA, one per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * kTcStages;      // [2] MMA -> epilogue, one per CTA (multicast commit)
+  uint64_t* tempty = bars + 2 * kTcStages + 2; // [2] epilogue warps of both CTAs -> MMA; the leader's copy
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();     // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(s_tmem);
+  if (warp == 1) tmem_alloc_pair<kTmemCols>(s_tmem);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -139,210 +239,250 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        int m_first, m_count, t0, t1, split;
-        decode_unit<EPI>(p, unit, m_first, m_count, t0, t1, split);
-        for (int mi = 0; mi < m_count; ++mi) {
-          for (int t = t0; t < t1; ++t) {
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              unsigned char* sa = smem + (size_t)stage * kStageBytes;
-              mbar_expect_tx(&full[stage], kStageBytes);
-              tma_load_2d(sa, &tmA, &full[stage], kb * kTcBK, (m_first + mi) * kTcBM);
-              tma_load_2d(sa + kABytes, &tmB, &full[stage], kb * kTcBK, t * kTcBN);
-              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-            }
+      Tile x;
+      for (bool have = first_tile<EPI>(p, pair, x); have; have = next_tile<EPI>(p, npairs, x)) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * kStageBytes;
+          const uint32_t leader_full = map_to_cta(smem_u32(&full[stage]), 0);
+          if (p.debug & 16) {
+            if (rank == 0) mbar_arrive(&full[stage]);
+          } else {
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes);   // bytes landing in both CTAs
+            tma_load_2d_pair(sa, &tmA, leader_full, kb * kTcBK, (x.m_base + (int)rank) * kTcBM);
+            tma_load_2d_pair(sa + kABytes, &tmB, leader_full, kb * kTcBK, x.t * kTcBN + (int)rank * (kTcBN / 2));
           }
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer ----
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kTcBN);
+    // -------------------------------------------------- MMA issuer (leader CTA) ----
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kTcBM, kTcBN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_count = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        int m_first, m_count, t0, t1, split;
-        decode_unit<EPI>(p, unit, m_first, m_count, t0, t1, split);
-        for (int mi = 0; mi < m_count; ++mi) {
-          for (int t = t0; t < t1; ++t, ++tile_count) {
-            const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-            mbar_wait(&tempty[buf], (use & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * kTcBN;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(&full[stage], phase);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
-              const uint32_t sb = sa + kABytes;
+      Tile x;
+      for (bool have = first_tile<EPI>(p, pair, x); have; have = next_tile<EPI>(p, npairs, x), ++tile_count) {
+        const uint32_t buf = tile_count & 1, use = tile_count >> 1;
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kTcBN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          if (!(p.debug & 32)) {
 #pragma unroll
-              for (int k4 = 0; k4 < kTcBK / 16; ++k4) {
-                umma_bf16(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
-                          (uint32_t)((kb | k4) != 0));
-              }
-              umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
-              if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            for (int k4 = 0; k4 < kTcBK / 16; ++k4) {
+              umma_bf16_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
+                             (uint32_t)((kb | k4) != 0));
             }
-            umma_commit(&tfull[buf]);      // accumulator ready for the epilogue
           }
+          umma_commit_pair(&empty[stage], 3);  // frees the slot in both CTAs once these MMAs retire
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
+        umma_commit_pair(&tfull[buf], 3);      // accumulators (both CTAs' TMEM) ready for the epilogues
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue ----
+    const int ew = warp - 2;                      // 0..7
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
+    const int chalf = ew >> 2;                    // which 128 columns of the tile this warp takes
     const int row_in_tile = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;              // 0..127
+    const int et = threadIdx.x - 64;              // 0..255: the tile column whose norm this thread stages
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t tempty_addr[2];
+    tempty_addr[0] = map_to_cta(smem_u32(&tempty[0]), 0);
+    tempty_addr[1] = map_to_cta(smem_u32(&tempty[1]), 0);
     uint32_t tile_count = 0;
     uint64_t list[HIPPO_TOPK_MAX];
 
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      int m_first, m_count, t0, t1, split;
-      decode_unit<EPI>(p, unit, m_first, m_count, t0, t1, split);
-      for (int mi = 0; mi < m_count; ++mi) {
-        const int64_t arow = (int64_t)(m_first + mi) * kTcBM + row_in_tile;  // query / row i
-        // ---- per-(unit, row) state
-        bool valid;
-        float an = 1.f;
-        uint64_t below = ~0ull;
-        float g_i = 0.f, b_i = 0.f;
+    // per-(unit, row) state
+    bool valid = false, force = false;
+    float an = 1.f, g_i = 0.f, b_i = 0.f;
+    uint64_t below = ~0ull;
+    int64_t arow = 0;
+    const float band = (EPI == EPI_MASK) ? ((p.inexact && *p.inexact) ? p.band_inexact : p.band_exact) : 0.f;
+
+    Tile cur;
+    bool have = first_tile<EPI>(p, pair, cur);
+    // prefetched for the tile about to be processed: its column norm (this thread's column), the row
+    // norm of the unit's row, and the global threshold
+    float pf_bn = 1.f, pf_rown = 0.f;
+    uint32_t pf_thr = 0;
+    auto prefetch = [&](const Tile& x) {
+      const int64_t col = (int64_t)x.t * kTcBN + et;
+      pf_bn = col < p.n ? p.bnorm[col] : 1.f;
+      const int64_t r = (int64_t)(x.m_base + (int)rank) * kTcBM + row_in_tile;
+      if constexpr (EPI == EPI_TOPK) {
+        if (x.first) pf_rown = r < p.nq ? p.qnorm[r] : 1.f;
+        pf_thr = r < p.nq ? __ldcg(&p.thr_ord[r]) : 0u;
+      } else {
+        if (x.first) pf_rown = r < p.n ? p.bnorm[r] : 0.f;
+      }
+    };
+    if (have) prefetch(cur);
+
+    while (have) {
+      const uint32_t buf = tile_count & 1, use = tile_count >> 1;
+      float* s_bn = s_cols + buf * 2 * kTcBN;
+      float* s_inv = s_bn + kTcBN;
+      const int t = cur.t;
+      if (cur.first) {
+        arow = (int64_t)(cur.m_base + (int)rank) * kTcBM + row_in_tile;
         if constexpr (EPI == EPI_TOPK) {
           valid = arow < p.nq;
-          if (valid) {
-            an = p.qnorm[arow];
-            if (p.after_key) below = p.after_key[arow];
-          }
+          an = pf_rown;
+          below = (valid && p.after_key) ? p.after_key[arow] : ~0ull;
+          force = valid && !(an > 0.f && an < INFINITY);   // zero / non-finite query: every score is NaN
 #pragma unroll
           for (int i = 0; i < HIPPO_TOPK_MAX; ++i) list[i] = 0;
         } else {
           valid = arow < p.n;
-          const float band = (p.inexact && *p.inexact) ? p.band_inexact : p.band_exact;
-          float ni = valid ? p.bnorm[arow] : 0.f;
-          const bool ok = ni > 0.f && !isinf(ni);
+          const float ni = valid ? pf_rown : 0.f;
+          const bool ok = ni > 0.f && ni < INFINITY;
           g_i = ok ? p.gamma * ni : -INFINITY;   // zero / non-finite row: every sim is NaN -> bit set
           b_i = ok ? band * ni : -1.f;
         }
+      }
+      // stage this tile's column norms (buffer `buf`; the barrier below also separates the writes from
+      // the reads of the tile two steps back).  Thread et covers column et, so a warp covers one
+      // 32-column chunk and a ballot yields the chunk's mask of "special" columns: zero / non-finite
+      // norms, whose similarity is NaN and must reach the exact path.
+      {
+        const int64_t col = (int64_t)t * kTcBN + et;
+        const bool in = col < p.n;
+        const float bn = pf_bn;
+        const bool special = in && !(bn > 0.f && bn < INFINITY);
+        s_bn[et] = bn;
+        s_inv[et] = in ? __frcp_rn(bn) : 0.f;
+        const uint32_t m = __ballot_sync(0xffffffffu, special);
+        if (lane == 0) s_spec[buf * 8 + ew] = m;
+      }
+      float thr = INFINITY;
+      if constexpr (EPI == EPI_TOPK) {
+        if (valid) {
+          uint64_t kth = list[p.k - 1];
+          const uint64_t g = (uint64_t)pf_thr << 32;
+          kth = g > kth ? g : kth;
+          thr = topk_filter_threshold(kth, an);
+        }
+      }
+      // next tile: issue its global loads now, they complete under this tile's math
+      Tile nxt = cur;
+      const bool have_next = next_tile<EPI>(p, npairs, nxt);
+      if (have_next) prefetch(nxt);
 
-        for (int t = t0; t < t1; ++t, ++tile_count) {
-          const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-          float* s_bn = s_cols + buf * 2 * kTcBN;
-          float* s_inv = s_bn + kTcBN;
-          // stage this tile's column norms (writes buffer `buf`; the barrier below also
-          // separates them from the reads of the tile two steps back)
-          for (int c = et; c < kTcBN; c += 128) {
-            const int64_t col = (int64_t)t * kTcBN + c;
-            const float bn = col < p.n ? p.bnorm[col] : 0.f;
-            s_bn[c] = bn;
-            s_inv[c] = col < p.n ? __frcp_rn(bn) : 0.f;
-          }
-          float thr = INFINITY;
-          if constexpr (EPI == EPI_TOPK) {
-            if (valid) {
-              uint64_t kth = list[p.k - 1];
-              const uint64_t g = (uint64_t)__ldcg(&p.thr_ord[arow]) << 32;
-              kth = g > kth ? g : kth;
-              thr = topk_filter_threshold(kth, an);
-            }
-          }
-          epi_bar_sync();
-          mbar_wait(&tfull[buf], use & 1);
-          tc_fence_after();
+      epi_bar_sync();
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
 
-          const uint32_t acc_addr = lane_addr + buf * kTcBN;
-          const int64_t col0 = (int64_t)t * kTcBN;
-          uint32_t ra[32], rb[32];
-          uint32_t words[8];
-          tmem_ld_32x32(acc_addr, ra);
+      const uint32_t acc_addr = lane_addr + buf * kTcBN + chalf * (kTcBN / 2);
+      const int64_t col0 = (int64_t)t * kTcBN + chalf * (kTcBN / 2);
+      uint32_t ra[32], rb[32];
+      uint32_t words[4] = {0u, 0u, 0u, 0u};
+      if (!(p.debug & 1)) {
+        tmem_ld_32x32(acc_addr, ra);
+        // two chunks per iteration: the TMEM load of one register set overlaps the arithmetic on the other
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
 #pragma unroll
-          for (int c = 0; c < kTcBN / 32; ++c) {
-            uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-            uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c = c2 * 2 + hh;            // chunk within this warp's 128 columns
+            uint32_t(&cur_r)[32] = hh ? rb : ra;
+            uint32_t(&nxt_r)[32] = hh ? ra : rb;
             tmem_ld_wait();
-            if (c + 1 < kTcBN / 32) tmem_ld_32x32(acc_addr + (c + 1) * 32, nxt);
-            const float* inv = s_inv + c * 32;
+            if (c + 1 < 4) tmem_ld_32x32(acc_addr + (c + 1) * 32, nxt_r);
+            const int cc = chalf * 4 + c;         // chunk within the tile
+            const float4* inv4 = reinterpret_cast<const float4*>(s_inv + cc * 32);
+            const uint32_t spec = s_spec[buf * 8 + cc];
             if constexpr (EPI == EPI_TOPK) {
-              bool hit = false;
+              // branch-free quick test: max over the chunk of dot / |b| against the row's threshold
+              float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float tv = __uint_as_float(cur[j]) * inv[j];
-                hit |= !(tv < thr);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 iv = inv4[j4];
+                m0 = fmaxf(m0, __uint_as_float(cur_r[4 * j4 + 0]) * iv.x);
+                m1 = fmaxf(m1, __uint_as_float(cur_r[4 * j4 + 1]) * iv.y);
+                m0 = fmaxf(m0, __uint_as_float(cur_r[4 * j4 + 2]) * iv.z);
+                m1 = fmaxf(m1, __uint_as_float(cur_r[4 * j4 + 3]) * iv.w);
               }
-              if (hit && valid) {
+              const float mx = fmaxf(m0, m1);
+              if (valid && (!(mx < thr) || spec != 0u || force)) {
+                float tmp[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float dot = __uint_as_float(cur[j]);
-                  const float tv = dot * inv[j];
-                  if (!(tv < thr)) {
-                    const int64_t col = col0 + c * 32 + j;
-                    if (col < p.n) {
-                      topk_consider(list, p.k, dot, s_bn[c * 32 + j], an,
-                                    (uint32_t)(p.row_base + col), below, &p.thr_ord[arow]);
-                      uint64_t kth = list[p.k - 1];
-                      const uint64_t g = (uint64_t)__ldcg(&p.thr_ord[arow]) << 32;
-                      kth = g > kth ? g : kth;
-                      thr = topk_filter_threshold(kth, an);
-                    }
-                  }
-                }
+                for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(cur_r[j]);
+                thr = topk_slow_chunk(tmp, s_inv + cc * 32, s_bn + cc * 32, col0 + c * 32, p.n, list, p.k, an,
+                                      p.row_base, below, &p.thr_ord[arow], p.pool + (size_t)arow * p.k, thr,
+                                      force);
               }
             } else {
+              // bit j = !(sim < gamma): sign bit of (dot/|b_j| - gamma |b_i|), shifted in from the top
               uint32_t w = 0;
               bool unc = false;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float tv = __uint_as_float(cur[j]) * inv[j];
-                w |= (!(tv < g_i)) ? (1u << j) : 0u;
-                unc |= fabsf(tv - g_i) <= b_i;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 iv = inv4[j4];
+                const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float d = fmaf(__uint_as_float(cur_r[4 * j4 + jj]), ivs[jj], -g_i);
+                  w = (w >> 1) | (~__float_as_uint(d) & 0x80000000u);
+                  unc |= fabsf(d) <= b_i;
+                }
               }
+              w |= spec;                                  // NaN similarity: `NaN < gamma` is False (hm:960)
               // keep pairs j < i only
               const int64_t jb = col0 + c * 32;
               uint32_t keep;
               if (!valid || jb >= arow) keep = 0u;
               else if (jb + 32 <= arow) keep = 0xffffffffu;
               else keep = (1u << (uint32_t)(arow - jb)) - 1u;
-              words[c] = w & keep;
+              if (c2 == 0) { if (hh == 0) words[0] = w & keep; else words[1] = w & keep; }
+              else { if (hh == 0) words[2] = w & keep; else words[3] = w & keep; }
               if (unc && keep) {
+                float tmp[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float tv = __uint_as_float(cur[j]) * inv[j];
-                  if ((fabsf(tv - g_i) <= b_i) && ((keep >> j) & 1u)) {
-                    const int pos = atomicAdd(p.uncertain_count, 1);
-                    if (pos < p.uncertain_cap)
-                      p.uncertain[pos] = make_uint2((uint32_t)arow, (uint32_t)(jb + j));
-                  }
-                }
+                for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(cur_r[j]);
+                mask_uncertain_chunk(tmp, s_inv + cc * 32, g_i, b_i, keep, (uint32_t)arow, (uint32_t)jb,
+                                     p.uncertain, p.uncertain_count, p.uncertain_cap);
               }
             }
           }
-          // TMEM buffer fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty[buf]);
-          if constexpr (EPI == EPI_MASK) {
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(p.mask + arow * p.words_per_row + (int64_t)t * 8);
-              dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
-              dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
-            }
-          }
-        }
-        if constexpr (EPI == EPI_TOPK) {
-          if (valid) {
-            uint64_t* dst = p.part + ((size_t)split * p.nq + arow) * p.k;
-            for (int i = 0; i < p.k; ++i) dst[i] = list[i];
-          }
         }
       }
+      // TMEM buffer fully read by this warp: one arrival per warp on the LEADER's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr[buf]);
+      if constexpr (EPI == EPI_MASK) {
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.mask + arow * p.words_per_row + (int64_t)t * 8 + chalf * 4);
+          *dst = make_uint4(words[0], words[1], words[2], words[3]);
+        }
+      } else {
+        const bool last = !have_next || nxt.first;
+        if (last && valid) {
+          uint64_t* dst = p.part + ((size_t)(cur.split * 2 + chalf) * p.nq + arow) * p.k;
+          for (int i = 0; i < p.k; ++i) dst[i] = list[i];
+        }
+      }
+      cur = nxt;
+      have = have_next;
+      ++tile_count;
     }
   }
 
+  // neither CTA may exit (or free TMEM) while its peer can still touch its shared memory / barriers
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 
@@ -389,35 +529,39 @@ static hippo_status make_tmap(CUtensorMap* tm, const void* base, int64_t rows, i
   return HIPPO_OK;
 }
 
+static int debug_flags() {
+  const char* e = getenv("HIPPO_TC_DEBUG");
+  return e ? atoi(e) : 0;
+}
+
 template <int EPI>
 static hippo_status launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   HIPPO_CUDA(cudaFuncSetAttribute(sim_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemBytes));
-  int grid = sm_count();
-  if (grid > p.units) grid = p.units;
-  if (grid < 1) return HIPPO_OK;
-  sim_tc_kernel<EPI><<<grid, kTcThreads, kSmemBytes, s>>>(tmA, tmB, p);
+  int pairs = sm_count() / 2;                 // one CTA per SM, two SMs per 256-row tile
+  if (pairs > p.units) pairs = p.units;
+  if (pairs < 1) return HIPPO_OK;
+  sim_tc_kernel<EPI><<<2 * pairs, kTcThreads, kSmemBytes, s>>>(tmA, tmB, p);
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
 
 int tc_topk_splits(int64_t n, int nq) {
-  const int sms = sm_count() > 0 ? sm_count() : 148;
-  const int m_blocks = (nq + kTcBM - 1) / kTcBM;
+  const int pairs = (sm_count() > 0 ? sm_count() : 148) / 2;
+  const int m_blocks = (nq + 2 * kTcBM - 1) / (2 * kTcBM);    // 256-query blocks
   const int64_t n_tiles = (n + kTcBN - 1) / kTcBN;
   if (n_tiles <= 0 || m_blocks <= 0) return 1;
-  // aim for units = m_blocks * splits ~ a multiple of the SM count, up to 8 waves,
-  // while keeping at least 8 tiles per split (the per-unit list start-up is not free)
+  // aim for units = m_blocks * splits ~ a multiple of the pair count, up to 8 waves
   int64_t best = 1;
   double best_cost = 1e300;
   for (int waves = 1; waves <= 8; ++waves) {
-    int64_t splits = ((int64_t)sms * waves + m_blocks - 1) / m_blocks;
+    int64_t splits = ((int64_t)pairs * waves + m_blocks - 1) / m_blocks;
     if (splits > n_tiles) splits = n_tiles;
     if (splits < 1) splits = 1;
     const int64_t tps = (n_tiles + splits - 1) / splits;
     const int64_t real_splits = (n_tiles + tps - 1) / tps;
     const int64_t units = real_splits * m_blocks;
-    const int64_t rounds = (units + sms - 1) / sms;
+    const int64_t rounds = (units + pairs - 1) / pairs;
     // cost = critical-path tiles + a small per-unit overhead
     const double cost = (double)rounds * (double)(tps + 2);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = real_splits; }
@@ -429,7 +573,7 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   hippo_status st = make_tmap(&tmA, a.qbf16, a.nq, a.d, kTcBM);
   if (st != HIPPO_OK) return st;
-  st = make_tmap(&tmB, a.bank, a.n, a.d, kTcBN);
+  st = make_tmap(&tmB, a.bank, a.n, a.d, kTcBN / 2);
   if (st != HIPPO_OK) return st;
   TcParams p{};
   p.n = a.n;
@@ -438,16 +582,18 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
   p.qnorm = a.qnorm;
   p.nq = a.nq;
   p.k = a.k;
-  p.m_blocks = (a.nq + kTcBM - 1) / kTcBM;
+  p.m_pairs = (a.nq + 2 * kTcBM - 1) / (2 * kTcBM);
   p.n_tiles = (int)((a.n + kTcBN - 1) / kTcBN);
   p.tiles_per_split = (p.n_tiles + a.splits - 1) / a.splits;
   p.splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   if (p.splits != a.splits) { set_error("tc_topk_launch: inconsistent split count"); return HIPPO_E_BADARG; }
-  p.units = p.m_blocks * p.splits;
+  p.units = p.m_pairs * p.splits;
   p.row_base = a.row_base;
   p.after_key = a.after_key;
   p.part = a.part;
   p.thr_ord = a.thr_ord;
+  p.pool = a.pool;
+  p.debug = debug_flags();
   return launch<EPI_TOPK>(tmA, tmB, p, s);
 }
 
@@ -455,7 +601,7 @@ hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   hippo_status st = make_tmap(&tmA, a.feats_bf16, a.n, a.d, kTcBM);
   if (st != HIPPO_OK) return st;
-  st = make_tmap(&tmB, a.feats_bf16, a.n, a.d, kTcBN);
+  st = make_tmap(&tmB, a.feats_bf16, a.n, a.d, kTcBN / 2);
   if (st != HIPPO_OK) return st;
   TcParams p{};
   p.n = a.n;
@@ -474,6 +620,7 @@ hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   p.uncertain = a.uncertain;
   p.uncertain_count = a.uncertain_count;
   p.uncertain_cap = a.uncertain_cap;
+  p.debug = debug_flags();
   return launch<EPI_MASK>(tmA, tmB, p, s);
 }
 

@@ -4,11 +4,11 @@
 
 namespace hippo {
 
-constexpr int kTcBM = 128;      // query / row-i block (TMEM lanes)
-constexpr int kTcBN = 256;      // bank / row-j block (TMEM columns)
+constexpr int kTcBM = 128;      // query / row-i block per CTA (TMEM lanes); a CTA pair covers 256
+constexpr int kTcBN = 256;      // bank / row-j block (TMEM columns); each CTA of the pair stages half
 constexpr int kTcBK = 64;       // bf16 elements per 128-byte swizzle row
-constexpr int kTcStages = 4;
-constexpr int kTcThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTcStages = 6;
+constexpr int kTcThreads = 320; // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 struct TcTopkArgs {
   const void* bank;          // [n, d] bf16
@@ -21,9 +21,10 @@ struct TcTopkArgs {
   int k;
   int64_t row_base;
   const uint64_t* after_key; // [nq] or null
-  uint64_t* part;            // [splits, nq, k]
+  uint64_t* part;            // [2 * splits, nq, k] (one list per bank split and column half)
   uint32_t* thr_ord;         // [nq], zero-initialised by the caller
-  int splits;                // bank splits (units = m_blocks * splits)
+  uint32_t* pool;            // [nq, k], zero-initialised by the caller
+  int splits;                // bank splits (units = 256-query blocks * splits)
 };
 // number of bank splits the launch will use for (n, nq) on this device
 int tc_topk_splits(int64_t n, int nq);

@@ -8,7 +8,8 @@ namespace hippo {
 struct BatchedLayout {
   __nv_bfloat16* qbf;
   float* qnorm;
-  uint32_t* thr_ord;
+  uint32_t* thr_ord;   // [nq] followed by the score pool [nq, k] (one memset clears both)
+  uint32_t* pool;
   uint64_t* part;
   int splits;
   size_t bytes;
@@ -19,9 +20,10 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   BatchedLayout L{};
   L.qbf = c.take<__nv_bfloat16>((size_t)nq * d);
   L.qnorm = c.take<float>((size_t)nq);
-  L.thr_ord = c.take<uint32_t>((size_t)nq);
+  L.thr_ord = c.take<uint32_t>((size_t)nq * (1 + (size_t)k));
+  L.pool = L.thr_ord ? L.thr_ord + nq : nullptr;
   L.splits = tc_topk_splits(n, nq);
-  L.part = c.take<uint64_t>((size_t)L.splits * nq * k);
+  L.part = c.take<uint64_t>((size_t)2 * L.splits * nq * k);
   L.bytes = c.used();
   return L;
 }
@@ -59,7 +61,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
     HIPPO_CUDA(cudaMemsetAsync(L.part, 0, (size_t)nq * k * 8, s));
     return hippo_topk_merge(L.part, 1, nq, k, k, out_idx, out_score, out_key, stream);
   }
-  HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, (size_t)nq * 4, s));
+  HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, (size_t)nq * (1 + (size_t)k) * 4, s));
   // queries -> bf16 + |a| (same pass the bank went through)
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
   if (st != HIPPO_OK) return st;
@@ -76,10 +78,11 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   a.after_key = after_key;
   a.part = L.part;
   a.thr_ord = L.thr_ord;
+  a.pool = L.pool;
   a.splits = L.splits;
   st = tc_topk_launch(a, s);
   if (st != HIPPO_OK) return st;
-  return hippo_topk_merge(L.part, L.splits, nq, k, k, out_idx, out_score, out_key, stream);
+  return hippo_topk_merge(L.part, 2 * L.splits, nq, k, k, out_idx, out_score, out_key, stream);
 }
 
 }  // extern "C"

@@ -52,12 +52,12 @@ def search_edge():
     b[3] = 0.0            # NaN similarity: np.argsort puts it last, i.e. first in the result
     b[9] = b[2]           # exact tie
     b[11] = -q            # similarity -1
-    b[5] = 2.5 * q        # similarity +1
+    b[5] = 2.0 * q        # similarity +1
     # bf16-representable values: the device bank holds bf16 rows, and at d = 64 the rounding of
     # arbitrary fp32 rows would move a score by up to ~1e-3 (it averages down to ~1e-4 at d = 1024)
     q = synth.round_to_bf16(q)
     b = synth.round_to_bf16(b)
-    b[9], b[11], b[5] = b[2], -q, 2.5 * q
+    b[9], b[11], b[5] = b[2], -q, 2.0 * q   # (power-of-two scale keeps the row bf16-exact)
     return b, q
 
 
