@@ -18,7 +18,7 @@ HIPPO_E_NCCL = -4
 HIPPO_E_WORKSPACE = -5
 
 HIPPO_F32, HIPPO_F64, HIPPO_BF16, HIPPO_I16 = 0, 1, 2, 3
-HIPPO_TOPK_MAX = 32
+HIPPO_TOPK_MAX = 16
 ABI_VERSION = 1
 
 

@@ -50,7 +50,8 @@ struct TcParams {
   int kblocks;        // d / 64
   const float* bnorm; // norms of B rows
   int units;
-  int debug;          // profiling knobs (HIPPO_TC_DEBUG): 1 = no epilogue math, 16 = no TMA loads, 32 = no MMAs
+  int debug;          // profiling knobs (HIPPO_TC_DEBUG): 1 = no epilogue at all, 2 = TMEM loads but no math,
+                      // 4 = no norm staging / barrier, 8 = never take the slow path, 16 = no TMA loads, 32 = no MMAs
   // top-k
   const float* qnorm;
   int nq, k, m_pairs /* 256-query blocks */, n_tiles, splits, tiles_per_split;
@@ -58,7 +59,10 @@ struct TcParams {
   const uint64_t* after_key;
   uint64_t* part;     // [2 * splits, nq, k]
   uint32_t* thr_ord;  // [nq]      global lower bound on the k-th best score (monotone, atomicMax)
-  uint32_t* pool;     // [nq, k]   global pool of the best scores seen by anyone (see pool_insert)
+  uint32_t* pool;     // [nq, k]   global pool of the best scores seen by anyone (see pool_update)
+  unsigned long long* counters;  // profiling (debug & 64): [0] slow-chunk calls, [1] insertions, [2] cycles in the
+                                 // slow path (per warp), [3] cycles epilogue warps wait for accumulators, [4] epilogue tiles x warps,
+                                 // [5] cycles the MMA thread waits for TMEM, [6] cycles it waits for operands
   // mask
   float gamma, band_exact, band_inexact;
   const int32_t* inexact;
@@ -126,74 +130,67 @@ __device__ __forceinline__ float topk_filter_threshold(uint64_t kth_key, float a
   return lo - fabsf(lo) * 9.5367431640625e-07f - 1e-37f;   // 2^-20 relative slack
 }
 
-// Global per-query pool of the k best score-ords any thread has inserted so far.  Insertion bubbles the
-// value down the k slots with atomicMax (slot keeps the larger, the smaller is carried on), which preserves
-// the multiset {pool} U {carried} at every step under any interleaving; every slot therefore always holds
-// the score of a DISTINCT eligible row, and min(pool) is a valid lower bound on the final k-th best score.
-// It is published through thr_ord (atomicMax), which only gates the approximate filter (with slack): results
-// do not depend on timing.
-__device__ __forceinline__ void pool_insert(uint32_t* pool_q, int k, uint32_t ord, uint32_t* thr_ord_q) {
-  uint32_t v = ord;
-  for (int j = 0; j < k && v != 0; ++j) {
-    const uint32_t old = atomicMax(&pool_q[j], v);
-    v = old < v ? old : v;
-  }
+// Global per-query score pool: k slots, a row goes to slot hash(row) % k, a slot keeps the best score-ord
+// hashed to it (fire-and-forget RED.MAX, no dependent round trips).  The k slots hold the scores of k
+// DISTINCT rows (different hash classes), so min(pool) is a valid lower bound on the final k-th best score,
+// under any interleaving.  It is published through thr_ord (RED.MAX, monotone), which only gates the
+// approximate filter (with slack): results do not depend on timing.  Returns the bound it published (0 = none).
+__device__ __forceinline__ uint32_t pool_update(uint32_t* pool_q, int k, uint32_t ord, uint32_t grow,
+                                                uint32_t* thr_ord_q) {
+  const int slot = (int)(((uint64_t)(grow * 2654435761u) * (uint32_t)k) >> 32);
+  atomicMax(&pool_q[slot], ord);
   uint32_t m = 0xffffffffu;
   for (int j = 0; j < k; ++j) {
-    const uint32_t g = __ldcg(&pool_q[j]);
+    uint32_t g = __ldcg(&pool_q[j]);
+    if (j == slot) g = g > ord ? g : ord;
     m = g < m ? g : m;
   }
   if (m != 0) atomicMax(thr_ord_q, m);
+  return m;
 }
 
-// Exact evaluation + list insertion of one candidate (rare path, kept out of line).
-__device__ __noinline__ void topk_consider(uint64_t* list, int k, float dot, float bn, float an,
-                                           uint32_t grow, uint64_t below, uint32_t* thr_ord_q,
-                                           uint32_t* pool_q) {
-  // the reference's operation order (vo:182): dot / (|b| * |a|), IEEE fp32
-  float s = __fdiv_rn(dot, __fmul_rn(bn, an));
-  uint64_t key = pack_key(s, grow);
-  if (key < below && key > list[k - 1]) {
-    topk_insert(list, k, key);
-    const uint32_t ord = (uint32_t)(key >> 32);
-    if (ord > __ldcg(thr_ord_q)) pool_insert(pool_q, k, ord, thr_ord_q);
-  }
-}
+// The per-thread top-k list lives in registers (kListRegs 64-bit entries, sorted descending; entries at
+// and beyond k stay 0): with ~210 KB of shared memory carved out the L1 is tiny, and a list in local memory
+// turned every insertion into a chain of L2 round trips (32k cycles per slow chunk, profiles/).
+constexpr int kListRegs = HIPPO_TOPK_MAX;
+static_assert(kListRegs == 16, "the register-resident top-k list is sized for HIPPO_TOPK_MAX == 16");
 
-// Rare path of the search epilogue: one 32-column chunk of one query row whose quick test fired.
-// `acc` is the thread's copy of the 32 accumulators (local memory); returns the updated filter threshold.
-__device__ __noinline__ float topk_slow_chunk(const float* acc, const float* inv, const float* bn, int64_t col0,
-                                              int64_t n, uint64_t* list, int k, float an, int64_t row_base,
-                                              uint64_t below, uint32_t* thr_ord_q, uint32_t* pool_q, float thr,
-                                              bool force) {
-  for (int j = 0; j < 32; ++j) {
-    const float dot = acc[j];
-    const float tv = dot * inv[j];
-    if (force || !(tv < thr)) {                          // NaN passes, as np.argsort ranks NaN first (vo:185)
-      const int64_t col = col0 + j;
-      if (col < n) {
-        topk_consider(list, k, dot, bn[j], an, (uint32_t)(row_base + col), below, thr_ord_q, pool_q);
-        uint64_t kth = list[k - 1];
-        const uint64_t g = (uint64_t)__ldcg(thr_ord_q) << 32;
-        kth = g > kth ? g : kth;
-        thr = topk_filter_threshold(kth, an);
-      }
+// Sorted insert by a compare-swap chain with static indices; the displaced tail value is dropped.
+__device__ __forceinline__ void list_insert(uint64_t (&L)[kListRegs], int k, uint64_t key) {
+  uint64_t v = key;
+#pragma unroll
+  for (int i = 0; i < kListRegs; ++i) {
+    if (i < k) {
+      const bool gt = v > L[i];
+      const uint64_t lo = gt ? L[i] : v;
+      L[i] = gt ? v : L[i];
+      v = lo;
     }
   }
-  return thr;
 }
-
-// Rare path of the consolidation epilogue: append the pairs of this chunk that sit inside the band.
-__device__ __noinline__ void mask_uncertain_chunk(const float* acc, const float* inv, float g_i, float b_i,
-                                                  uint32_t keep, uint32_t arow, uint32_t jb, uint2* uncertain,
-                                                  int32_t* count, int32_t cap) {
-  for (int j = 0; j < 32; ++j) {
-    const float d = fmaf(acc[j], inv[j], -g_i);
-    if ((fabsf(d) <= b_i) && ((keep >> j) & 1u)) {
-      const int pos = atomicAdd(count, 1);
-      if (pos < cap) uncertain[pos] = make_uint2(arow, jb + j);
-    }
+// list[k-1]: the list is sorted descending with zeros in unused slots, so that is the minimum of the first
+// k entries (written as a reduction so the compiler cannot turn it into an indexed local-memory load).
+__device__ __forceinline__ uint64_t list_kth(const uint64_t (&L)[kListRegs], int k) {
+  uint64_t r = ~0ull;
+#pragma unroll
+  for (int i = 0; i < kListRegs; ++i) {
+    const uint64_t v = (i < k) ? L[i] : ~0ull;
+    r = v < r ? v : r;
   }
+  return r;
+}
+// r[j] for a run-time j without local memory: a 5-level select tree over the 32 registers.
+__device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -266,11 +263,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       Tile x;
       for (bool have = first_tile<EPI>(p, pair, x); have; have = next_tile<EPI>(p, npairs, x), ++tile_count) {
         const uint32_t buf = tile_count & 1, use = tile_count >> 1;
+        long long tw = (p.debug & 64) ? clock64() : 0;
         mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        if (p.debug & 64) atomicAdd(&p.counters[5], (unsigned long long)(clock64() - tw));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kTcBN;
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          tw = (p.debug & 64) ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (p.debug & 64) atomicAdd(&p.counters[6], (unsigned long long)(clock64() - tw));
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
@@ -299,7 +300,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tempty_addr[0] = map_to_cta(smem_u32(&tempty[0]), 0);
     tempty_addr[1] = map_to_cta(smem_u32(&tempty[1]), 0);
     uint32_t tile_count = 0;
-    uint64_t list[HIPPO_TOPK_MAX];
+    uint64_t list[kListRegs];
+    uint64_t kth_key = 0;                     // list[k-1], kept alongside so the hot path never indexes the list
 
     // per-(unit, row) state
     bool valid = false, force = false;
@@ -340,7 +342,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           below = (valid && p.after_key) ? p.after_key[arow] : ~0ull;
           force = valid && !(an > 0.f && an < INFINITY);   // zero / non-finite query: every score is NaN
 #pragma unroll
-          for (int i = 0; i < HIPPO_TOPK_MAX; ++i) list[i] = 0;
+          for (int i = 0; i < kListRegs; ++i) list[i] = 0;
+          kth_key = 0;
         } else {
           valid = arow < p.n;
           const float ni = valid ? pf_rown : 0.f;
@@ -353,7 +356,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // the reads of the tile two steps back).  Thread et covers column et, so a warp covers one
       // 32-column chunk and a ballot yields the chunk's mask of "special" columns: zero / non-finite
       // norms, whose similarity is NaN and must reach the exact path.
-      {
+      if (!(p.debug & 4)) {
         const int64_t col = (int64_t)t * kTcBN + et;
         const bool in = col < p.n;
         const float bn = pf_bn;
@@ -364,12 +367,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (lane == 0) s_spec[buf * 8 + ew] = m;
       }
       float thr = INFINITY;
+      const uint32_t gthr = pf_thr;          // global bound on the k-th best score as of the last tile
       if constexpr (EPI == EPI_TOPK) {
         if (valid) {
-          uint64_t kth = list[p.k - 1];
           const uint64_t g = (uint64_t)pf_thr << 32;
-          kth = g > kth ? g : kth;
-          thr = topk_filter_threshold(kth, an);
+          thr = topk_filter_threshold(g > kth_key ? g : kth_key, an);
         }
       }
       // next tile: issue its global loads now, they complete under this tile's math
@@ -377,9 +379,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const bool have_next = next_tile<EPI>(p, npairs, nxt);
       if (have_next) prefetch(nxt);
 
-      epi_bar_sync();
+      if (!(p.debug & 4)) epi_bar_sync();
+      long long t_wait0 = 0, t_chunk = 0;
+      if (p.debug & 64) t_wait0 = clock64();
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
+      if (p.debug & 64) {
+        t_chunk = clock64();
+        if (lane == 0) { atomicAdd(&p.counters[3], (unsigned long long)(t_chunk - t_wait0)); atomicAdd(&p.counters[4], 1ull); }
+      }
 
       const uint32_t acc_addr = lane_addr + buf * kTcBN + chalf * (kTcBN / 2);
       const int64_t col0 = (int64_t)t * kTcBN + chalf * (kTcBN / 2);
@@ -398,6 +406,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tmem_ld_wait();
             if (c + 1 < 4) tmem_ld_32x32(acc_addr + (c + 1) * 32, nxt_r);
             const int cc = chalf * 4 + c;         // chunk within the tile
+            if (p.debug & 2) continue;
             const float4* inv4 = reinterpret_cast<const float4*>(s_inv + cc * 32);
             const uint32_t spec = s_spec[buf * 8 + cc];
             if constexpr (EPI == EPI_TOPK) {
@@ -412,13 +421,53 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 m1 = fmaxf(m1, __uint_as_float(cur_r[4 * j4 + 3]) * iv.w);
               }
               const float mx = fmaxf(m0, m1);
-              if (valid && (!(mx < thr) || spec != 0u || force)) {
-                float tmp[32];
+              if (valid && (!(mx < thr) || spec != 0u || force) && !(p.debug & 8)) {
+                // rare path, all in registers: mask of the columns that pass, then one candidate at a time
+                uint32_t hits = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(cur_r[j]);
-                thr = topk_slow_chunk(tmp, s_inv + cc * 32, s_bn + cc * 32, col0 + c * 32, p.n, list, p.k, an,
-                                      p.row_base, below, &p.thr_ord[arow], p.pool + (size_t)arow * p.k, thr,
-                                      force);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 iv = inv4[j4];
+                  const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const float tv = __uint_as_float(cur_r[4 * j4 + jj]) * ivs[jj];
+                    hits |= (!(tv < thr)) ? (1u << (4 * j4 + jj)) : 0u;   // NaN passes (vo:185 ranks NaN first)
+                  }
+                }
+                if (force) hits = 0xffffffffu;
+                uint32_t gord = gthr;
+                uint32_t n_calls = 0;
+                while (hits) {
+                  const int j = __ffs(hits) - 1;
+                  hits &= hits - 1;
+                  const int64_t col = col0 + c * 32 + j;
+                  if (col >= p.n) continue;
+                  const float dot = __uint_as_float(select32(cur_r, j));
+                  if (!force && (dot * s_inv[cc * 32 + j] < thr)) continue;     // threshold moved meanwhile
+                  // the reference's operation order (vo:182): dot / (|b| * |a|), IEEE fp32
+                  const float sc = __fdiv_rn(dot, __fmul_rn(s_bn[cc * 32 + j], an));
+                  const uint32_t grow = (uint32_t)(p.row_base + col);
+                  const uint64_t key = pack_key(sc, grow);
+                  if (key < below && key > kth_key) {
+                    list_insert(list, p.k, key);
+                    kth_key = list_kth(list, p.k);
+                    ++n_calls;
+                    const uint32_t ord = (uint32_t)(key >> 32);
+                    if (ord > gord) {
+                      const uint32_t m = pool_update(p.pool + (size_t)arow * p.k, p.k, ord, grow, &p.thr_ord[arow]);
+                      gord = m > gord ? m : gord;
+                    }
+                    const uint64_t g = (uint64_t)gord << 32;
+                    thr = topk_filter_threshold(g > kth_key ? g : kth_key, an);
+                  }
+                }
+                if (p.debug & 64) { atomicAdd(&p.counters[0], 1ull); atomicAdd(&p.counters[1], (unsigned long long)n_calls); }
+              }
+              if (p.debug & 64) {   // cycles of chunks that took the slow path (a fast chunk is < 400 clk)
+                __syncwarp();
+                const long long t_now = clock64();
+                if (lane == 0 && t_now - t_chunk > 400) atomicAdd(&p.counters[2], (unsigned long long)(t_now - t_chunk));
+                t_chunk = t_now;
               }
             } else {
               // bit j = !(sim < gamma): sign bit of (dot/|b_j| - gamma |b_i|), shifted in from the top
@@ -445,11 +494,21 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (c2 == 0) { if (hh == 0) words[0] = w & keep; else words[1] = w & keep; }
               else { if (hh == 0) words[2] = w & keep; else words[3] = w & keep; }
               if (unc && keep) {
-                float tmp[32];
+                // rare path: pairs inside the band go to the uncertain list (re-evaluated from fp32 rows)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(cur_r[j]);
-                mask_uncertain_chunk(tmp, s_inv + cc * 32, g_i, b_i, keep, (uint32_t)arow, (uint32_t)jb,
-                                     p.uncertain, p.uncertain_count, p.uncertain_cap);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 iv = inv4[j4];
+                  const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * j4 + jj;
+                    const float d = fmaf(__uint_as_float(cur_r[j]), ivs[jj], -g_i);
+                    if ((fabsf(d) <= b_i) && ((keep >> j) & 1u)) {
+                      const int pos = atomicAdd(p.uncertain_count, 1);
+                      if (pos < p.uncertain_cap) p.uncertain[pos] = make_uint2((uint32_t)arow, (uint32_t)(jb + j));
+                    }
+                  }
+                }
               }
             }
           }
@@ -468,7 +527,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const bool last = !have_next || nxt.first;
         if (last && valid) {
           uint64_t* dst = p.part + ((size_t)(cur.split * 2 + chalf) * p.nq + arow) * p.k;
-          for (int i = 0; i < p.k; ++i) dst[i] = list[i];
+#pragma unroll
+          for (int i = 0; i < kListRegs; ++i)
+            if (i < p.k) dst[i] = list[i];
         }
       }
       cur = nxt;
@@ -593,6 +654,7 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
   p.part = a.part;
   p.thr_ord = a.thr_ord;
   p.pool = a.pool;
+  p.counters = a.counters;
   p.debug = debug_flags();
   return launch<EPI_TOPK>(tmA, tmB, p, s);
 }

@@ -24,6 +24,7 @@ struct TcTopkArgs {
   uint64_t* part;            // [2 * splits, nq, k] (one list per bank split and column half)
   uint32_t* thr_ord;         // [nq], zero-initialised by the caller
   uint32_t* pool;            // [nq, k], zero-initialised by the caller
+  unsigned long long* counters;  // [8] profiling counters (only touched with HIPPO_TC_DEBUG & 64)
   int splits;                // bank splits (units = 256-query blocks * splits)
 };
 // number of bank splits the launch will use for (n, nq) on this device

@@ -10,6 +10,7 @@ struct BatchedLayout {
   float* qnorm;
   uint32_t* thr_ord;   // [nq] followed by the score pool [nq, k] (one memset clears both)
   uint32_t* pool;
+  unsigned long long* counters;   // [8], first thing in the workspace so a profiling script can find it
   uint64_t* part;
   int splits;
   size_t bytes;
@@ -18,6 +19,7 @@ struct BatchedLayout {
 static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d, int nq, int k) {
   Carver c(ws, ws_bytes);
   BatchedLayout L{};
+  L.counters = c.take<unsigned long long>(8);
   L.qbf = c.take<__nv_bfloat16>((size_t)nq * d);
   L.qnorm = c.take<float>((size_t)nq);
   L.thr_ord = c.take<uint32_t>((size_t)nq * (1 + (size_t)k));
@@ -79,6 +81,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   a.part = L.part;
   a.thr_ord = L.thr_ord;
   a.pool = L.pool;
+  a.counters = L.counters;
   a.splits = L.splits;
   st = tc_topk_launch(a, s);
   if (st != HIPPO_OK) return st;

@@ -50,7 +50,7 @@ typedef int32_t hippo_status;
 
 /* Largest k one search launch keeps per query (larger k: the host wrapper
  * calls again with the `after_*` cursor, see hippo_topk_*).                 */
-#define HIPPO_TOPK_MAX 32
+#define HIPPO_TOPK_MAX 16
 
 /* ---- library ------------------------------------------------------------ */
 int32_t      hippo_abi_version(void);
@@ -88,7 +88,7 @@ hippo_status hippo_bank_build(const void* rows, int32_t dtype, int64_t n, int32_
  *   row_base    added to local row numbers in out_idx (shard offset)
  *   after_key   optional uint64[nq] cursor: only rows ordered strictly AFTER
  *               this packed (score,row) key are considered (NULL = all rows).
- *               Pass out_key of the previous call to page through k > 32.
+ *               Pass out_key of the previous call to page through k > HIPPO_TOPK_MAX.
  *   out_idx     [nq, k] int64, -1 where fewer than k rows qualify
  *   out_score   [nq, k] fp32
  *   out_key     optional [nq, k] uint64 packed order keys (0 = empty slot);

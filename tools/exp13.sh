@@ -1,0 +1,2 @@
+python tools/prof_counters.py
+QUERIES=random python tools/prof_counters.py
