@@ -26,6 +26,7 @@ SOURCES = [
     "bank_build.cu",
     "topk_single.cu",
     "topk_batched.cu",
+    "recall.cu",
     "sim_tc.cu",
     "consolidate.cu",
     "frames.cu",

@@ -250,6 +250,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, ui
       "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same with an L2 cache-policy operand (createpolicy encodings as CUTLASS's TMA::CacheHintSm90).
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const void* tmap, uint32_t bar_cluster_addr,
+                                                      int32_t c0, int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

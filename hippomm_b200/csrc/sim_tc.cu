@@ -60,6 +60,8 @@ struct TcParams {
   uint64_t* part;     // [2 * splits, nq, k]
   uint32_t* thr_ord;  // [nq]      global lower bound on the k-th best score (monotone, atomicMax)
   uint32_t* pool;     // [nq, k]   global pool of the best scores seen by anyone (see pool_update)
+  uint32_t* prog;     // [units]   tiles whose loads each unit's leader has started (flow control, see the producer)
+  int fc_window;      // a pair may run at most this many tiles ahead of the slowest pair of its cohort (0 = off)
   unsigned long long* counters;  // profiling (debug & 64): [0] slow-chunk calls, [1] insertions, [2] cycles in the
                                  // slow path (per warp), [3] cycles epilogue warps wait for accumulators, [4] epilogue tiles x warps,
                                  // [5] cycles the MMA thread waits for TMEM, [6] cycles it waits for operands
@@ -89,11 +91,29 @@ __device__ __forceinline__ void decode_unit(const TcParams& p, int unit, int& m_
     t0 = split * p.tiles_per_split;
     t1 = min(t0 + p.tiles_per_split, p.n_tiles);
   } else {
-    // lower triangle of 256 x 256 blocks: unit = I(I+1)/2 + t, t <= I
-    int I = (int)((sqrtf(8.f * (float)unit + 1.f) - 1.f) * 0.5f);
-    while ((int64_t)(I + 1) * (I + 2) / 2 <= unit) ++I;
-    while ((int64_t)I * (I + 1) / 2 > unit) --I;
-    t0 = unit - (int)((int64_t)I * (I + 1) / 2);
+    // lower triangle of 256 x 256 blocks (t <= I), enumerated in BANDS of kBand row blocks: inside a band the
+    // column tile t varies slowest, so the pairs running concurrently share ~9 column tiles and the band's
+    // kBand row blocks; every column tile is then fetched from HBM once per band instead of once per row block.
+    constexpr int kBand = 8;
+    const int nI = p.n_tiles;                         // row blocks = column tiles
+    // units before band b: sum_{b'<b} (64 b' + 36) = 32 b^2 + 4 b   (full bands of 8 row blocks)
+    int b = (int)((sqrtf(16.f + 128.f * (float)unit) - 4.f) * (1.f / 64.f));
+    while ((int64_t)32 * (b + 1) * (b + 1) + 4 * (b + 1) <= unit) ++b;
+    while ((int64_t)32 * b * b + 4 * b > unit) --b;
+    const int h = min(kBand, nI - kBand * b);         // height of this band (the last one may be short)
+    int r = unit - (32 * b * b + 4 * b);
+    const int full = (kBand * b + 1) * h;             // t = 0 .. 8b: all h row blocks
+    int I;
+    if (r < full) {
+      t0 = r / h;
+      I = kBand * b + (r - t0 * h);
+    } else {
+      r -= full;                                      // tail: t = 8b + 1 + j has h - 1 - j row blocks
+      int j = 0;
+      while (r >= h - 1 - j) { r -= h - 1 - j; ++j; }
+      t0 = kBand * b + 1 + j;
+      I = t0 + r;
+    }
     t1 = t0 + 1;
     m_base = 2 * I;
     split = 0;
@@ -233,11 +253,50 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer ----
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      Tile x;
-      for (bool have = first_tile<EPI>(p, pair, x); have; have = next_tile<EPI>(p, npairs, x)) {
+    // Lane 0 issues the loads.  Flow control (top-k only): the pairs whose units cover the same bank split in
+    // the same round (a "cohort", up to m_pairs pairs) stream the same bank tiles; left alone they drift apart
+    // (SMs far from an L2 slice run ~10% slower) until a tile is evicted before the last pair asks for it, and
+    // the bank was read from HBM ~8x per step (profiles/).  Every leader therefore publishes how many tiles it
+    // has started and does not run more than fc_window tiles ahead of the slowest member of its cohort.  The
+    // counters only delay loads: results do not depend on them.
+    int stage = 0;
+    uint32_t phase = 0;
+    Tile x;
+    int tiu = 0, u_lo = 0, u_hi = 0;
+    uint32_t known_min = 0;
+    const bool fc = EPI == EPI_TOPK && p.fc_window > 0 && rank == 0 && p.prog != nullptr;
+    for (bool have = first_tile<EPI>(p, pair, x); have; have = next_tile<EPI>(p, npairs, x)) {
+      if (fc) {
+        if (x.first) {
+          tiu = 0;
+          known_min = 0;
+          const int round = x.unit / npairs;
+          u_lo = max(x.split * p.m_pairs, round * npairs);
+          u_hi = min(min((x.split + 1) * p.m_pairs, (round + 1) * npairs), p.units);
+        }
+        ++tiu;
+        if (lane == 0) *(volatile uint32_t*)&p.prog[x.unit] = (uint32_t)tiu;
+        const int need = tiu - p.fc_window;
+        if (need > 0 && known_min < (uint32_t)need) {
+          uint32_t m;
+          for (;;) {
+            m = 0xffffffffu;
+            for (int u = u_lo + lane; u < u_hi; u += 32) {
+              const uint32_t v = *(volatile const uint32_t*)&p.prog[u];
+              m = v < m ? v : m;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const uint32_t other = __shfl_xor_sync(0xffffffffu, m, o);
+              m = other < m ? other : m;
+            }
+            if (m >= (uint32_t)need) break;
+            __nanosleep(256);
+          }
+          known_min = m;
+        }
+      }
+      if (lane == 0) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * kStageBytes;
@@ -252,6 +311,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // -------------------------------------------------- MMA issuer (leader CTA) ----
@@ -590,6 +650,12 @@ static hippo_status make_tmap(CUtensorMap* tm, const void* base, int64_t rows, i
   return HIPPO_OK;
 }
 
+// Flow-control window in tiles (HIPPO_TC_WINDOW overrides; 0 disables).
+static int flow_window() {
+  const char* e = getenv("HIPPO_TC_WINDOW");
+  return e ? atoi(e) : 8;
+}
+
 static int debug_flags() {
   const char* e = getenv("HIPPO_TC_DEBUG");
   return e ? atoi(e) : 0;
@@ -655,6 +721,8 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
   p.thr_ord = a.thr_ord;
   p.pool = a.pool;
   p.counters = a.counters;
+  p.prog = a.progress;
+  p.fc_window = flow_window();
   p.debug = debug_flags();
   return launch<EPI_TOPK>(tmA, tmB, p, s);
 }
@@ -670,6 +738,7 @@ hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   p.kblocks = a.d / kTcBK;
   p.bnorm = a.norm;
   const int64_t nI = (a.n + kTcBN - 1) / kTcBN;
+  p.n_tiles = (int)nI;
   const int64_t units = nI * (nI + 1) / 2;
   if (units > 0x7fffffffll) { set_error("tc_mask_launch: n too large"); return HIPPO_E_BADARG; }
   p.units = (int)units;

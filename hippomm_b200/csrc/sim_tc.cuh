@@ -25,6 +25,7 @@ struct TcTopkArgs {
   uint32_t* thr_ord;         // [nq], zero-initialised by the caller
   uint32_t* pool;            // [nq, k], zero-initialised by the caller
   unsigned long long* counters;  // [8] profiling counters (only touched with HIPPO_TC_DEBUG & 64)
+  uint32_t* progress;        // [256-query blocks * splits], zero-initialised by the caller (flow control)
   int splits;                // bank splits (units = 256-query blocks * splits)
 };
 // number of bank splits the launch will use for (n, nq) on this device

@@ -8,8 +8,10 @@ namespace hippo {
 struct BatchedLayout {
   __nv_bfloat16* qbf;
   float* qnorm;
-  uint32_t* thr_ord;   // [nq] followed by the score pool [nq, k] (one memset clears both)
-  uint32_t* pool;
+  uint32_t* thr_ord;   // [nq] followed by the score pool [nq, k] and the per-unit progress counters
+  uint32_t* pool;      // (one memset clears all three)
+  uint32_t* progress;
+  size_t clear_words;
   unsigned long long* counters;   // [8], first thing in the workspace so a profiling script can find it
   uint64_t* part;
   int splits;
@@ -22,9 +24,12 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   L.counters = c.take<unsigned long long>(8);
   L.qbf = c.take<__nv_bfloat16>((size_t)nq * d);
   L.qnorm = c.take<float>((size_t)nq);
-  L.thr_ord = c.take<uint32_t>((size_t)nq * (1 + (size_t)k));
-  L.pool = L.thr_ord ? L.thr_ord + nq : nullptr;
   L.splits = tc_topk_splits(n, nq);
+  const size_t units = (size_t)((nq + 2 * kTcBM - 1) / (2 * kTcBM)) * (size_t)L.splits;
+  L.clear_words = (size_t)nq * (1 + (size_t)k) + units;
+  L.thr_ord = c.take<uint32_t>(L.clear_words);
+  L.pool = L.thr_ord ? L.thr_ord + nq : nullptr;
+  L.progress = L.thr_ord ? L.thr_ord + (size_t)nq * (1 + (size_t)k) : nullptr;
   L.part = c.take<uint64_t>((size_t)2 * L.splits * nq * k);
   L.bytes = c.used();
   return L;
@@ -63,7 +68,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
     HIPPO_CUDA(cudaMemsetAsync(L.part, 0, (size_t)nq * k * 8, s));
     return hippo_topk_merge(L.part, 1, nq, k, k, out_idx, out_score, out_key, stream);
   }
-  HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, (size_t)nq * (1 + (size_t)k) * 4, s));
+  HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, L.clear_words * 4, s));
   // queries -> bf16 + |a| (same pass the bank went through)
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
   if (st != HIPPO_OK) return st;
@@ -82,6 +87,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   a.thr_ord = L.thr_ord;
   a.pool = L.pool;
   a.counters = L.counters;
+  a.progress = L.progress;
   a.splits = L.splits;
   st = tc_topk_launch(a, s);
   if (st != HIPPO_OK) return st;

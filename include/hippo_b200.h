@@ -122,6 +122,49 @@ hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, 
                               int32_t k, int64_t* out_idx, float* out_score, uint64_t* out_key,
                               void* stream);
 
+/* ---- detailed recall over all events at once ------ */
+/*
+ * The reference searches event by event: `for event in long_term_store:
+ * top_k_cosine_similarity(query, event.features[modality], k=5)` (hm:3143-3153,
+ * hm:3295-3304).  Here every event's rows sit in ONE bank and `seg_offsets`
+ * [nseg+1] (int64, ascending, seg_offsets[0] = 0, seg_offsets[nseg] = n) marks
+ * the events, so one streaming pass serves the whole store.
+ *
+ * hippo_scores_single: out_score[row] = dot / (norm_b * norm_a) for every row
+ * (fp32, IEEE division, the operation order of vo:182).
+ */
+hippo_status hippo_scores_single(const void* bank, const float* norm, int64_t n, int32_t d,
+                                 const float* q, float* out_score, void* stream);
+/*
+ * hippo_topk_segmented: the pass above into the workspace, then the k best rows of
+ * every event (score descending, NaN first, lower row first on ties).
+ *   out_idx    [nseg, k] int64 event-LOCAL row numbers, -1 where the event has fewer than k rows
+ *   out_score  [nseg, k] fp32
+ *   out_max    optional [nseg] fp32: max of the event's top-k as np.max sees it
+ *              (hm:3156 / hm:3307 compare it with 0.4 to route an event to the LLM path)
+ */
+size_t       hippo_topk_segmented_workspace_bytes(int64_t n);
+hippo_status hippo_topk_segmented(const void* bank, const float* norm, int64_t n, int32_t d,
+                                  const float* q, const int64_t* seg_offsets, int32_t nseg, int32_t k,
+                                  int64_t* out_idx, float* out_score, float* out_max,
+                                  void* ws, size_t ws_bytes, void* stream);
+/*
+ * Tail of the recall loop (hm:3258-3277, hm:3366-3381): candidate (event e, rank r)
+ * is live iff enabled[e] (NULL = all), idx >= 0 and idx < time_offsets[e+1]-time_offsets[e]
+ * (the `idx < len(event.frame_times)` guard of hm:3262, which applies all-frame indices to
+ * the key-frame time table); the m best live candidates by similarity (stable: earlier
+ * event, then better rank, first -- Python's sort with reverse=True) come back with their
+ * windows [max(0, t - pad), t + pad].
+ *   times        fp64, all events' time tables concatenated; time_offsets [nseg+1] int64
+ *   out_event    [m] int32 (-1 = unused slot), out_idx [m] int64, out_score [m] fp32,
+ *   out_window   [m, 2] fp64 (start, end), out_count int32* (live entries written)
+ */
+hippo_status hippo_recall_windows(const int64_t* seg_idx, const float* seg_score, int32_t nseg, int32_t k,
+                                  const int64_t* time_offsets, const double* times,
+                                  const uint8_t* enabled, double pad, int32_t m,
+                                  int32_t* out_event, int64_t* out_idx, float* out_score,
+                                  double* out_window, int32_t* out_count, void* stream);
+
 /* ---- memory consolidation (hm:944-967 _select_key_frames) --------------- */
 /*
  * Greedy redundancy filter: row 0 is kept; row i is kept iff
