@@ -14,6 +14,8 @@ from __future__ import annotations
 from . import _lib
 from .bank import MemoryBank
 from .consolidation import select_key_frames, select_key_frames_device
+from .events import EventBank, find_relevant_segments
+from .prefilter import dedup_window_frames, select_saved_frames
 from .segmentation import (SequenceSegment, compute_audio_level, compute_frame_difference,
                            compute_frame_similarity, segment_sequence)
 from .vector_ops import cosine_similarity, set_bank_cache, top_k_cosine_similarity
@@ -23,7 +25,8 @@ __version__ = "0.1.0"
 __all__ = [
     "MemoryBank", "SequenceSegment", "top_k_cosine_similarity", "cosine_similarity", "select_key_frames",
     "select_key_frames_device", "segment_sequence", "compute_frame_similarity", "compute_audio_level",
-    "compute_frame_difference", "install", "uninstall", "library_path",
+    "compute_frame_difference", "EventBank", "find_relevant_segments", "select_saved_frames", "dedup_window_frames",
+    "install", "uninstall", "library_path",
 ]
 
 _saved = {}

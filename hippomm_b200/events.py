@@ -227,9 +227,9 @@ class EventBank:
 
         bank = MemoryBank(meta["n"], meta["d"], device=device)
         if meta["n"]:
-            rows = torch.from_numpy(np.ascontiguousarray(section("rows_bf16")).view(np.int16))
+            rows = torch.from_numpy(np.array(section("rows_bf16")).view(np.int16))
             bank.rows[: meta["n"]].view(torch.int16).copy_(rows.to(bank.device))
-            bank.norm[: meta["n"]].copy_(torch.from_numpy(np.ascontiguousarray(section("norm_f32"))).to(bank.device))
+            bank.norm[: meta["n"]].copy_(torch.from_numpy(np.array(section("norm_f32"))).to(bank.device))
             bank._inexact.fill_(1)     # the fp32 originals are gone: treat as not bf16-exact
         return cls(bank, np.array(section("offsets")), np.array(section("time_offsets")), np.array(section("times")),
                    np.array(section("event_index")), meta.get("modality", "vision"))

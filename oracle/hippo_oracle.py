@@ -365,3 +365,85 @@ def adjacent_ssim(frames_bgr: np.ndarray) -> np.ndarray:
         g1, g2 = grays[p + 1], grays[p]
         out[p] = structural_similarity(g1, g2, data_range=g1.max() - g1.min())
     return out
+
+
+# =====================================================================  detailed recall  ==
+def find_relevant_segments(query: np.ndarray, events, modality: str = "vision", top: int = 5, k: int = 5,
+                           pad: float = 1.0):
+    """Similarity path of `_find_relevant_video_segments` (hm:3129-3279, modality "vision") and
+    `_find_relevant_audio_segments` (hm:3281-3383, modality "audio"): per event top-k (hm:3153 /
+    hm:3304), windows around the hits whose index is inside the event's time table (hm:3258-3272 /
+    hm:3366-3377), stable sort by similarity, best `top` (hm:3274-3277 / hm:3379-3381).  The LLM
+    branch (taken when the best similarity is below 0.4 AND the event has captions / a transcription)
+    is outside the arithmetic path; events here carry neither.
+
+    `events`: objects with .features[modality] (n_e, d), .frame_times / .frames (vision) or
+    .feature_times['audio_times'] (audio).  Returns a list of dicts
+    {start, end, similarity, event, index, frames, frame_times}."""
+    q = np.asarray(query).reshape(-1)                                        # hm:3132-3136
+    similarity_segments = []
+    for ei, event in enumerate(events):
+        if modality not in event.features:                                   # hm:3144 / hm:3296
+            continue
+        feats = np.asarray(event.features[modality])
+        idxs, sims = top_k_cosine_similarity(q, feats, k)
+        if modality == "vision":
+            times = list(event.frame_times)
+        else:
+            times = list(event.feature_times["audio_times"])
+        for idx, sim in zip(idxs, sims):
+            if idx < len(times):                                             # hm:3262 / hm:3367
+                t = times[idx]
+                seg = dict(start=max(0, t - pad), end=t + pad, similarity=sim, event=ei, index=int(idx))
+                if modality == "vision":                                     # hm:3267-3270
+                    seg["frames"] = [event.frames[i] for i in range(len(event.frames))
+                                     if times[i] >= t - pad and times[i] <= t + pad]
+                    seg["frame_times"] = [x for x in times if x >= t - pad and x <= t + pad]
+                similarity_segments.append((sim, seg))
+    similarity_segments.sort(key=lambda x: x[0], reverse=True)               # hm:3274 / hm:3379
+    return [seg for _, seg in similarity_segments[:top]]
+
+
+# =====================================================================  greedy frame filters  ==
+def select_saved_frames(frames: np.ndarray, video_fps: float, max_diff_threshold: float = 0.3,
+                        check_interval: int = 30):
+    """The save decisions of extract_frames_from_video (bp:179-228) on already decoded frames
+    (cv2.VideoCapture / imwrite are the caller's I/O).  Returns (frame numbers, times)."""
+    frame_numbers, frame_times = [], []
+    last_saved_frame = None
+    cumulative_diff = 0.0
+    last_save_time = 0.0
+    for frame_count, frame in enumerate(frames):                               # bp:179-182
+        current_time = frame_count / video_fps                                 # bp:184
+        save = False
+        if last_saved_frame is None:                                           # bp:187-188
+            save = True
+        elif current_time - last_save_time >= 1.0:                             # bp:190
+            if frame_count % check_interval == 0:                              # bp:192
+                diff = compute_frame_difference(frame, last_saved_frame)       # bp:194
+                cumulative_diff += diff                                        # bp:195
+                if diff > max_diff_threshold or cumulative_diff > max_diff_threshold:   # bp:198-200
+                    save = True
+        if save:                                                               # bp:202-219
+            frame_numbers.append(frame_count)
+            frame_times.append(current_time)
+            last_saved_frame = frame
+            cumulative_diff = 0.0
+            last_save_time = current_time
+    return frame_numbers, frame_times
+
+
+def dedup_window_frames(frames: np.ndarray, threshold: float = 0.3) -> List[int]:
+    """The de-duplication inside one QA re-decode window (hm:2226-2249 with 0.3; hm:2789-2812 with 0.4):
+    a frame is dropped when `_compute_frame_similarity(prev_kept, frame) > threshold` (hm:2237-2238)."""
+    kept: List[int] = []
+    prev = None
+    for i, frame in enumerate(frames):
+        if prev is not None:
+            with np.errstate(all="ignore"):
+                similarity = compute_frame_similarity(frames[prev], frame)
+            if similarity > threshold:
+                continue
+        kept.append(i)
+        prev = i
+    return kept

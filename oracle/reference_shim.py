@@ -99,12 +99,22 @@ def load():
         m.audio_silence_threshold = audio_silence_threshold
         return m
 
+    def make_recall_system(events):
+        """QARecallSystem (hm:1615) with only the long-term store set: enough for the similarity path of
+        _find_relevant_video_segments / _find_relevant_audio_segments (hm:3127-3383)."""
+        r = object.__new__(hm.QARecallSystem)
+        r.memory = types.SimpleNamespace(long_term_store=list(events))
+        r._current_question = ""
+        return r
+
     _loaded.update(
+        make_recall_system=make_recall_system,
         top_k_cosine_similarity=vo.top_k_cosine_similarity,
         cosine_similarity=vo.cosine_similarity,
         HippocampalMemory=hm.HippocampalMemory,
         SequenceSegment=hm.SequenceSegment,
         compute_frame_difference=bp.compute_frame_difference,
+        extract_frames_from_video=bp.extract_frames_from_video,
         make_memory=make_memory,
         modules=(vo, hm, bp),
     )

@@ -138,3 +138,125 @@ def segmentation_variants():
         "av_short": dict(video=True, audio=True, thresholds=short),
         "v_short": dict(video=True, audio=False, thresholds=short),
     }
+
+
+# ------------------------------------------------------------------ recall ----
+class _Event:
+    """The fields of the reference's ThetaEvent (hm:95-108) that the recall loops read."""
+
+    def __init__(self, features, feature_times, frames, frame_times):
+        self.features = features
+        self.feature_times = feature_times
+        self.frames = frames
+        self.frame_times = frame_times
+        self.frame_captions = []                     # falsy: the LLM branch of hm:3156 / hm:3307 is never taken
+        self.audio_times = []
+        self.audio_transcription = []
+        self.holistic_audio_transcription = []
+        self.summary = ""
+        self.start_time = frame_times[0] if frame_times else 0.0
+        self.end_time = frame_times[-1] if frame_times else 0.0
+
+
+@functools.lru_cache(maxsize=None)
+def recall_events():
+    """14 events of 3..90 all-frame vision rows (1024-d, video-like) with SHORTER key-frame time tables
+    (the index-space quirk of hm:3262), audio rows with their own times, one event without audio and one
+    with fewer than 5 rows; two queries planted near rows of events 3 and 9."""
+    rng = np.random.default_rng(77)
+    events, t0 = [], 0.0
+    sizes = [40, 3, 25, 60, 12, 90, 7, 33, 5, 48, 20, 4, 70, 16]
+    for e, n in enumerate(sizes):
+        vis = synth.videolike_features(1000 + e, max(1, n // 10), min(n, 10))[:n]
+        if len(vis) < n:
+            vis = np.concatenate([vis, synth.videolike_features(2000 + e, 1, n - len(vis))])
+        n_key = max(1, int(n * (0.3 + 0.5 * rng.random())))        # key frames: a subset, so some hits fall outside
+        all_times = t0 + np.arange(n, dtype=np.float64)
+        key_times = sorted(rng.choice(all_times, size=n_key, replace=False).tolist())
+        feats = {"vision": vis.astype(np.float32)}
+        ftimes = {"vision_times": all_times.copy()}
+        if e != 6:
+            na = max(2, n // 3)
+            feats["audio"] = synth.videolike_features(3000 + e, 1, na, step=0.4).astype(np.float32)
+            ftimes["audio_times"] = t0 + 3.0 * np.arange(na, dtype=np.float64) + 0.5
+        frames = [f"/frames/e{e:02d}_{i:04d}.jpg" for i in range(n_key)]
+        events.append(_Event(feats, ftimes, frames, key_times))
+        t0 += n + 5.0
+    d = 1024
+    noise = lambda: np.float32(0.2) * rng.standard_normal(d).astype(np.float32)
+    queries = {
+        # hits inside the key-frame table of one event
+        "v_in": ("vision", events[3].features["vision"][7] + noise()),
+        # planted at the LAST all-frame row of the 90-row event: beyond its key-frame table, dropped by hm:3262
+        "v_out": ("vision", events[5].features["vision"][89] + noise()),
+        # between two events: the final five mix events
+        "v_mix": ("vision", events[7].features["vision"][4] + events[12].features["vision"][30] + noise()),
+        "a_in": ("audio", events[9].features["audio"][2] + noise()),
+        "a_mix": ("audio", events[2].features["audio"][1] + events[13].features["audio"][3] + noise()),
+    }
+    return events, {k: (m, q.astype(np.float32)) for k, (m, q) in queries.items()}
+
+
+# ----------------------------------------------------------- greedy frame filters ----
+@functools.lru_cache(maxsize=None)
+def prefilter_frames():
+    """360 frames of 96 x 96 BGR 'decoded at 30 fps' (12 s): scenes of 1-3 s with a slow brightness drift
+    inside each scene, so that both the single-difference and the cumulative trigger of bp:198-200 fire."""
+    base, cuts = synth.frame_stream(21, 12, 96, 96, min_scene=1, max_scene=3)
+    rng = np.random.default_rng(22)
+    frames = np.empty((360, 96, 96, 3), dtype=np.uint8)
+    for i in range(360):
+        f = base[i // 30].astype(np.int16)
+        drift = int(round(2.5 * (i % 90) / 10.0))
+        noise = rng.integers(-2, 3, size=f.shape, dtype=np.int16)
+        frames[i] = np.clip(f + drift + noise, 0, 255).astype(np.uint8)
+    return frames
+
+
+PREFILTER_PARAMS = dict(video_fps=30.0, max_diff_threshold=0.3, check_interval=10)
+
+
+def write_mjpg(frames, path, fps=30.0):
+    """Write frames as an MJPG AVI with OpenCV's built-in encoder (no ffmpeg needed)."""
+    import cv2
+
+    h, w = frames.shape[1:3]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), fps, (w, h))
+    if not wr.isOpened():
+        return False
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    return True
+
+
+def read_video(path):
+    import cv2
+
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        out.append(f)
+    cap.release()
+    return np.stack(out) if out else np.zeros((0, 1, 1, 3), dtype=np.uint8)
+
+
+@functools.lru_cache(maxsize=None)
+def dedup_windows():
+    """Windows of 3-6 frames of 180 x 320 (the size hm:2230 resizes to): near-duplicates and changes."""
+    sc = [synth.frame_stream(31 + s, 1, 180, 320)[0][0] for s in range(4)]
+    blend = np.clip(0.3 * sc[0].astype(np.float64) + 0.7 * sc[1], 0, 255).astype(np.uint8)   # SSIM to sc[0] ~ 0.36:
+    rng = np.random.default_rng(32)                                                           # dropped at 0.3, kept at 0.4
+    wins = []
+    for order in ([0, 0, 1], [1, 2, 2, 3], [3, 3, 3], [0, 1, 0, 1, 1, 2], [0, "b", 1], [0, "b", "b", 0]):
+        fr = []
+        for j in order:
+            src = blend if j == "b" else sc[j]
+            f = src.astype(np.int16) + rng.integers(-1, 2, size=src.shape, dtype=np.int16)
+            fr.append(np.clip(f, 0, 255).astype(np.uint8))
+        wins.append(np.stack(fr))
+    wins.append(np.stack([np.full((180, 320, 3), 9, np.uint8)] * 3))   # constant frames: SSIM is NaN, nothing dropped
+    return wins

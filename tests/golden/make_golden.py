@@ -109,6 +109,38 @@ def main() -> None:
             out[f"seg_{tag}_nframes"] = np.array([len(s.frames) if s.frames is not None else -1 for s in segs])
             out[f"seg_{tag}_nsamples"] = np.array([len(s.audio_data) if s.audio_data is not None else -1 for s in segs])
 
+    # ---- detailed recall: the reference's own loops over a synthetic long-term store (hm:3127-3383) ----
+    import torch
+
+    events, queries = cases.recall_events()
+    rs = ref.make_recall_system(events)
+    for name, (modality, q) in queries.items():
+        fn = rs._find_relevant_video_segments if modality == "vision" else rs._find_relevant_audio_segments
+        segs = fn(torch.from_numpy(q))
+        out[f"recall_{name}_bounds"] = np.array([[s.start_time, s.end_time] for s in segs], dtype=np.float64).reshape(-1, 2)
+        if modality == "vision":
+            out[f"recall_{name}_nframes"] = np.array([len(s.frames) for s in segs], dtype=np.int64)
+            out[f"recall_{name}_frame_times"] = np.array([t for s in segs for t in s.frame_times], dtype=np.float64)
+
+    # ---- key-frame pre-filter: the reference's own extract_frames_from_video (bp:116-260) on an MJPG AVI ----
+    import hashlib
+    import pathlib
+    import re
+
+    pf = cases.prefilter_frames()
+    with tempfile.TemporaryDirectory() as td:
+        avi = os.path.join(td, "v.avi")
+        assert cases.write_mjpg(pf, avi, cases.PREFILTER_PARAMS["video_fps"])
+        decoded = cases.read_video(avi)
+        assert len(decoded) == len(pf)
+        paths, times, duration = ref.extract_frames_from_video(
+            avi, pathlib.Path(td) / "store", "vid", config={}, max_diff_threshold=cases.PREFILTER_PARAMS["max_diff_threshold"],
+            check_interval=cases.PREFILTER_PARAMS["check_interval"])
+        out["prefilter_frame_numbers"] = np.array([int(re.search(r"frame_(\d+)\.jpg", p).group(1)) for p in paths], dtype=np.int64)
+        out["prefilter_frame_times"] = np.array(times, dtype=np.float64)
+        # fingerprint of the DECODED frames: the committed decisions only apply if the test box decodes the same pixels
+        out["prefilter_decoded_sha1"] = np.frombuffer(hashlib.sha1(decoded.tobytes()).digest(), dtype=np.uint8)
+
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")

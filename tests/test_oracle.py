@@ -177,3 +177,38 @@ def test_live_reference_agrees_with_restatements():
     assert [(s.start_time, s.end_time) for s in segs] == O.segment_boundaries(None, None, x, 16000)
     fr, _ = synth.frame_stream(5, 4, 40, 48, min_scene=2, max_scene=2)
     assert ref.compute_frame_difference(fr[0], fr[2]) == O.compute_frame_difference(fr[0], fr[2])
+
+
+def test_recall_restatement_matches_reference_outputs():
+    """hm:3127-3383 (similarity path) restated vs the committed outputs of the reference's own functions."""
+    events, queries = cases.recall_events()
+    g = cases.golden()
+    for name, (modality, q) in queries.items():
+        segs = O.find_relevant_segments(q, events, modality)
+        bounds = np.array([[s["start"], s["end"]] for s in segs], dtype=np.float64).reshape(-1, 2)
+        assert np.array_equal(bounds, g[f"recall_{name}_bounds"]), name
+        if modality == "vision":
+            assert [len(s["frames"]) for s in segs] == g[f"recall_{name}_nframes"].tolist()
+            assert [t for s in segs for t in s["frame_times"]] == g[f"recall_{name}_frame_times"].tolist()
+
+
+def _decoded_prefilter_frames(tmp_path):
+    import hashlib
+
+    avi = str(tmp_path / "v.avi")
+    if not cases.write_mjpg(cases.prefilter_frames(), avi, cases.PREFILTER_PARAMS["video_fps"]):
+        pytest.skip("OpenCV cannot write MJPG here")
+    decoded = cases.read_video(avi)
+    sha = np.frombuffer(hashlib.sha1(decoded.tobytes()).digest(), dtype=np.uint8)
+    if not np.array_equal(sha, cases.golden()["prefilter_decoded_sha1"]):
+        pytest.skip("this OpenCV build decodes the MJPG stream to different pixels than the golden run")
+    return decoded
+
+
+def test_prefilter_restatement_matches_reference_outputs(tmp_path):
+    """bp:179-228 restated vs the committed decisions of the reference's own extract_frames_from_video."""
+    decoded = _decoded_prefilter_frames(tmp_path)
+    g = cases.golden()
+    numbers, times = O.select_saved_frames(decoded, **cases.PREFILTER_PARAMS)
+    assert numbers == g["prefilter_frame_numbers"].tolist()
+    assert times == g["prefilter_frame_times"].tolist()
