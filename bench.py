@@ -45,6 +45,24 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_json_out = None
+
+
+def capture_stdout():
+    """Stdout must carry the ONE JSON line only: libraries (NCCL prints its version banner there) get stderr."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -179,7 +197,7 @@ def run_reference_arm(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------ GPU arm ----
@@ -249,7 +267,7 @@ def run_gpu_arm(args):
             entry.build()
     barrier()
     from hippomm_b200 import MemoryBank, _cuda, _lib, synth
-    from hippomm_b200.distributed import gather_keys, merge_keys, shard_range
+    from hippomm_b200.distributed import PeerExchange, gather_keys, merge_keys, shard_range
 
     lib = _lib.load()
     peaks = load_peaks()
@@ -273,14 +291,35 @@ def run_gpu_arm(args):
     ws = _cuda.workspace(ws_bytes, device, "topk")
     stream = _cuda.stream_ptr()
 
+    # the exchange of the sharded search: the fused push + merge kernel over peer memory, unless the symmetric
+    # buffers cannot be set up (then: NCCL all-gather + merge).  HIPPO_EXCHANGE=nccl forces the latter.
+    peer = None
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl"
+        if os.environ.get("HIPPO_EXCHANGE", "p2p") != "nccl":
+            try:
+                peer = PeerExchange(NQ, 16, device)
+                exchange = "p2p"
+            except Exception as e:
+                log(f"[rank {rank}] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+        flag = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer, exchange = None, "nccl"
+
+    def exchange_merge(kk):
+        if peer is not None:
+            return peer.exchange_merge(kk, k)
+        return merge_keys(gather_keys(kk), k)
+
     def step_device():
         """C-ABI call on device-resident inputs (+ the exchange when sharded)."""
         _lib.check(lib.hippo_topk_batched(bank.rows.data_ptr(), bank.norm.data_ptr(), n_local, DIM, q_dev.data_ptr(),
                                           NQ, k, lo, None, idx.data_ptr(), score.data_ptr(), key.data_ptr(),
                                           ws.data_ptr(), ws.numel(), stream))
         if world > 1:
-            g = gather_keys(key)
-            return merge_keys(g, k)
+            return exchange_merge(key)
         return idx, score, key
 
     out_idx_host = torch.empty((NQ, k), dtype=torch.int64).pin_memory()
@@ -291,7 +330,7 @@ def run_gpu_arm(args):
         if world > 1:
             qd = q_pinned.to(device, non_blocking=True)
             _, _, kk = bank.search_keys(qd, k, "batched")
-            i2, s2, _ = merge_keys(gather_keys(kk), k)
+            i2, s2, _ = exchange_merge(kk)
         else:
             i2, s2 = bank.search(q_pinned, k, "batched")
         out_idx_host.copy_(i2, non_blocking=True)
@@ -346,7 +385,10 @@ def run_gpu_arm(args):
             "workload": f"batched feature search: {NQ} queries top-{k} over a {n_total}x{DIM} memory bank "
                         f"(bf16 rows + fp32 norms resident in HBM, {n_local} rows per GPU)",
             "bank_rows": n_total, "dim": DIM, "queries_per_step": NQ, "k": k,
-            "parallelism": f"bank rows sharded over {world} GPU(s); all-gather of (score,row) keys + replicated merge",
+            "parallelism": f"bank rows sharded over {world} GPU(s); "
+                           + {"none": "single shard", "p2p": "keys pushed to peers over NVLink and merged in one fused kernel",
+                              "nccl": "NCCL all-gather of (score,row) keys + replicated merge"}[exchange],
+            "exchange": exchange,
             "l2": "inputs_exceed_l2 (20.5 GB bank streamed per step; no explicit flush needed)",
             "generator": "counter-based lattice bank (bf16-exact), seed 4",
         },
@@ -366,7 +408,7 @@ def run_gpu_arm(args):
         line["cpu_baseline"] = None
     barrier()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -527,6 +569,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -76,6 +76,8 @@ SIGNATURES = {
     "hippo_topk_batched_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I32]),
     "hippo_topk_batched": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "hippo_topk_merge": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "hippo_topk_exchange_bytes": (_SZ, [_I32, _I32, _I32]),
+    "hippo_topk_exchange_merge": (_I32, [_P, _I32, _I32, _I32, _P, _SZ, _I32, _I32, C.c_uint32, _P, _P, _P, _P]),
     "hippo_scores_single": (_I32, [_P, _P, _I64, _I32, _P, _P, _P]),
     "hippo_topk_segmented_workspace_bytes": (_SZ, [_I64]),
     "hippo_topk_segmented": (_I32, [_P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),

@@ -27,6 +27,7 @@ SOURCES = [
     "topk_single.cu",
     "topk_batched.cu",
     "recall.cu",
+    "exchange.cu",
     "sim_tc.cu",
     "consolidate.cu",
     "frames.cu",

@@ -41,7 +41,8 @@ constexpr int kEpiThreads = kTcThreads - 64;              // 256
 constexpr int kEpiWarps = kEpiThreads / 32;               // 8
 constexpr size_t kSmemTiles = (size_t)kTcStages * kStageBytes;
 constexpr size_t kSmemColF = 2 * 2 * kTcBN * sizeof(float);           // [buf][norm|inv][256]
-constexpr size_t kSmemCols = kSmemColF + 2 * 8 * sizeof(uint32_t);    // + [buf][8] special-column masks
+constexpr size_t kSmemSpec = 2 * 8 * sizeof(uint32_t);                // [buf][8] special-column masks
+constexpr size_t kSmemCols = kSmemColF + kSmemSpec + 2 * 8 * 2 * sizeof(float);   // + [buf][8][min|max] chunk norm range
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kSmemTiles + kSmemCols + 256 /*barriers*/;
 
 struct TcParams {
@@ -213,6 +214,11 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100
+  return r;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int EPI>
@@ -225,6 +231,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_cols = reinterpret_cast<float*>(smem + kSmemTiles);                     // [buf][2][256]
   uint32_t* s_spec = reinterpret_cast<uint32_t*>(smem + kSmemTiles + kSmemColF);   // [buf][8]
+  float* s_bmm = reinterpret_cast<float*>(smem + kSmemTiles + kSmemColF + kSmemSpec);   // [buf][8][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles + kSmemCols);
   uint64_t* full = bars;                       // [stages] TMA (both CTAs) -> MMA; the leader's copy is used
   uint64_t* empty = bars + kTcStages;          // [stages] MMA -> TMA, one per CTA (multicast commit)
@@ -424,6 +431,17 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         s_bn[et] = bn;
         s_inv[et] = in ? __frcp_rn(bn) : 0.f;
         const uint32_t m = __ballot_sync(0xffffffffu, special);
+        if constexpr (EPI == EPI_TOPK) {
+          // smallest / largest ordinary norm of the chunk: dot/|b| >= thr needs max(dot) >= thr * |b|_min
+          // (thr > 0) or thr * |b|_max (thr <= 0), so the quick test below needs no per-element multiply
+          float lo = (in && !special) ? bn : INFINITY, hi = (in && !special) ? bn : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+          }
+          if (lane == 0) { s_bmm[(buf * 8 + ew) * 2] = lo; s_bmm[(buf * 8 + ew) * 2 + 1] = hi; }
+        }
         if (lane == 0) s_spec[buf * 8 + ew] = m;
       }
       float thr = INFINITY;
@@ -470,18 +488,17 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const float4* inv4 = reinterpret_cast<const float4*>(s_inv + cc * 32);
             const uint32_t spec = s_spec[buf * 8 + cc];
             if constexpr (EPI == EPI_TOPK) {
-              // branch-free quick test: max over the chunk of dot / |b| against the row's threshold
-              float m0 = -INFINITY, m1 = -INFINITY;
+              // branch-free quick test: max over the chunk of the raw dots against thr * (extreme norm of the chunk)
+              float m0 = __uint_as_float(cur_r[0]), m1 = __uint_as_float(cur_r[1]);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 iv = inv4[j4];
-                m0 = fmaxf(m0, __uint_as_float(cur_r[4 * j4 + 0]) * iv.x);
-                m1 = fmaxf(m1, __uint_as_float(cur_r[4 * j4 + 1]) * iv.y);
-                m0 = fmaxf(m0, __uint_as_float(cur_r[4 * j4 + 2]) * iv.z);
-                m1 = fmaxf(m1, __uint_as_float(cur_r[4 * j4 + 3]) * iv.w);
+              for (int j = 2; j < 32; j += 4) {
+                m0 = fmax3(m0, __uint_as_float(cur_r[j]), __uint_as_float(cur_r[j + 1]));
+                if (j + 2 < 32) m1 = fmax3(m1, __uint_as_float(cur_r[j + 2]), __uint_as_float(cur_r[j + 3]));
               }
+              const float2 bmm = *reinterpret_cast<const float2*>(&s_bmm[(buf * 8 + cc) * 2]);
               const float mx = fmaxf(m0, m1);
-              if (valid && (!(mx < thr) || spec != 0u || force) && !(p.debug & 8)) {
+              const float bound = thr * (thr > 0.f ? bmm.x : bmm.y);
+              if (valid && (!(mx < bound) || spec != 0u || force) && !(p.debug & 8)) {
                 // rare path, all in registers: mask of the columns that pass, then one candidate at a time
                 uint32_t hits = 0;
 #pragma unroll

@@ -51,17 +51,81 @@ def merge_keys(gathered: torch.Tensor, k: int):
     return idx, score, key
 
 
+class PeerExchange:
+    """Symmetric gather buffers for `hippo_topk_exchange_merge`: one allocation per rank, mapped into every
+    process of the group (torch symmetric memory: CUDA VMM handles exchanged once at rendezvous), so the
+    merge kernel stores its keys straight into the peers' HBM over NVLink.  Sized for (nq_cap, k_cap)."""
+
+    def __init__(self, nq_cap: int, k_cap: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        lib = _lib.load()
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.nq_cap, self.k_cap = int(nq_cap), int(k_cap)
+        self.nbytes = int(lib.hippo_topk_exchange_bytes(self.world, self.nq_cap, self.k_cap))
+        with torch.cuda.device(device):
+            self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, self.group.group_name)
+            torch.cuda.synchronize()
+        self.handle.barrier()              # every rank's buffer is cleared before anyone pushes
+        self.epoch = 0
+
+    def fits(self, nq: int, k: int) -> bool:
+        return _lib.load().hippo_topk_exchange_bytes(self.world, nq, k) <= self.nbytes
+
+    def exchange_merge(self, keys: torch.Tensor, k: int):
+        """keys: this rank's order keys [nq, k_in] (int64 bit patterns). Returns (idx, score, key) [nq, k]."""
+        lib = _lib.load()
+        dev = keys.device
+        nq, k_in = keys.shape
+        idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        score = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        key = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        self.epoch += 1
+        with torch.cuda.device(dev):
+            _lib.check(lib.hippo_topk_exchange_merge(
+                keys.contiguous().data_ptr(), nq, k_in, k, self.handle.buffer_ptrs_dev, self.nbytes, self.rank,
+                self.world, self.epoch, idx.data_ptr(), score.data_ptr(), key.data_ptr(), _cuda.stream_ptr()))
+        return idx, score, key
+
+
 class ShardedBank:
-    """This rank's shard of an n_total-row bank plus the collective search over all shards."""
+    """This rank's shard of an n_total-row bank plus the collective search over all shards.
+
+    exchange = "p2p"  : the fused push + merge kernel over peer memory (`hippo_topk_exchange_merge`);
+               "nccl" : one all-gather of the keys, then `hippo_topk_merge` (also what the CPU/gloo tests drive);
+               "auto" : p2p on CUDA when the symmetric buffers can be set up, else nccl.
+    """
 
     def __init__(self, n_total: int, d: int, device=None, group=None, rank: Optional[int] = None,
-                 world: Optional[int] = None):
+                 world: Optional[int] = None, exchange: str = "auto"):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.n_total, self.d = int(n_total), int(d)
         self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
         self.local = MemoryBank(self.hi - self.lo, d, device=device, row_base=self.lo)
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.exchange = exchange
+        self._peer: Optional[PeerExchange] = None
+        self._peer_failed: Optional[str] = None
+
+    def _peer_exchange(self, nq: int, k: int) -> Optional[PeerExchange]:
+        if self.exchange == "nccl" or self.world == 1 or self._peer_failed:
+            return None
+        if self._peer is None or not self._peer.fits(nq, k):
+            try:
+                # collective: every rank reaches this with the same (nq, k)
+                self._peer = PeerExchange(max(nq, 4096), max(k, _lib.HIPPO_TOPK_MAX), self.local.device, self.group)
+            except Exception as e:  # no peer access / symmetric memory unavailable
+                if self.exchange == "p2p":
+                    raise
+                self._peer_failed = f"{type(e).__name__}: {e}"
+                return None
+        return self._peer
 
     def fill_local(self, start_local: int, rows) -> None:
         self.local.fill(start_local, rows)
@@ -74,6 +138,10 @@ class ShardedBank:
         if self.world == 1:
             gathered = keys.unsqueeze(0)
         else:
+            peer = self._peer_exchange(keys.shape[0], k)
+            if peer is not None:
+                idx, score, _ = peer.exchange_merge(keys, k)
+                return idx, score
             gathered = gather_keys(keys, self.group)
         idx, score, _ = merge_keys(gathered, k)
         return idx, score

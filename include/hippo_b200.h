@@ -122,6 +122,24 @@ hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, 
                               int32_t k, int64_t* out_idx, float* out_score, uint64_t* out_key,
                               void* stream);
 
+/*
+ * Sharded search, collective fused into the merge: every rank's kernel pushes its
+ * out_key block [nq, k_in] into slot [rank] of EVERY rank's gather buffer through peer-mapped
+ * pointers (NVLink stores, no NCCL call), publishes an epoch flag, waits for the flags of all
+ * ranks in its own buffer and merges world x k_in candidates per query.  All ranks obtain the
+ * identical result, equal to hippo_topk_merge over an all-gather of the same keys.
+ *   peer_bases  DEVICE array [world] of pointers: base of rank r's exchange buffer as mapped into
+ *               THIS process (one symmetric allocation of hippo_topk_exchange_bytes() bytes per rank,
+ *               zero-filled once before the first call; e.g. torch symmetric memory's buffer_ptrs_dev)
+ *   epoch       1, 2, 3, ... incremented by every rank on every call (selects one of two gather buffers)
+ * Every rank of the group must make the matching call; the kernel spins until its peers' have run.
+ */
+size_t       hippo_topk_exchange_bytes(int32_t world, int32_t nq, int32_t k);
+hippo_status hippo_topk_exchange_merge(const uint64_t* local_keys, int32_t nq, int32_t k_in, int32_t k,
+                                       void* const* peer_bases, size_t buf_bytes, int32_t rank, int32_t world,
+                                       uint32_t epoch, int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                       void* stream);
+
 /* ---- detailed recall over all events at once ------ */
 /*
  * The reference searches event by event: `for event in long_term_store:

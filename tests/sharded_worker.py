@@ -1,0 +1,51 @@
+"""Worker for tests/test_gpu_sharded.py (launched with torchrun, one process per GPU): the sharded search
+with the fused peer-memory exchange must equal the NCCL all-gather path and the single-GPU answer."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    from hippomm_b200 import MemoryBank, synth
+    from hippomm_b200.distributed import ShardedBank
+
+    n, d, nq, k = 40_000, 1024, 300, 10
+    rows = synth.lattice_rows_np(4, np.arange(n), d, n)
+    q, fam = synth.lattice_queries_np(4, nq, d, n)
+    results = {}
+    for exchange in ("p2p", "nccl"):
+        sb = ShardedBank(n, d, exchange=exchange)
+        sb.fill_local(0, rows[sb.lo:sb.hi])
+        for rep in range(5):                                   # repeated calls alternate the two gather buffers
+            qs = q if rep % 2 == 0 else q[::-1].copy()
+            idx, score = sb.search(qs, k)
+            if rep % 2 == 1:
+                idx, score = idx.flip(0), score.flip(0)
+            results.setdefault(exchange, []).append((idx.cpu().numpy(), score.cpu().numpy()))
+        one, _ = sb.search(q[:1], k)                           # single-query (GEMV) path through the same exchange
+        assert np.array_equal(one.cpu().numpy()[0], results[exchange][0][0][0])
+    full = MemoryBank.from_rows(rows)
+    fi, fs = full.search(q, k, "batched")
+    fi, fs = fi.cpu().numpy(), fs.cpu().numpy()
+    for exchange, reps in results.items():
+        for idx, score in reps:
+            assert np.array_equal(idx, fi), f"{exchange}: rows differ from the single-GPU answer"
+            assert np.array_equal(score.view(np.uint32), fs.view(np.uint32)), f"{exchange}: scores differ"
+    assert np.array_equal(np.sort(fi, axis=1), synth.lattice_expected_topk(fam, n, k))
+    dist.barrier()
+    if rank == 0:
+        print("SHARDED_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
