@@ -52,99 +52,137 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
 }
 
 // ---- 4. greedy scan over the bit matrix ------------------------------------------------
-// CTA b owns rows [512 b, 512 b + 512).  It ANDs its rows' mask words against the final
-// kept-words of earlier blocks as those become final (ordered chain through `ready`), then
-// one warp resolves the 512 x 512 diagonal block 32 rows at a time.
+// CTA b owns rows [512 b, 512 b + 512).  The chain over blocks is sequential (a row's fate depends on
+// which earlier rows were KEPT), so the kernel is bound by the hand-off latency between consecutive
+// blocks; everything that does not depend on the predecessor's result is done ahead of it:
+//   * kept-words are published as self-validating 64-bit values (tag << 32 | word), so a consumer polls
+//     the data itself -- one L2 round trip per hand-off, no separate flag, no fence;
+//   * the mask columns of the two preceding blocks and the 512 x 512 diagonal block are staged in
+//     shared memory before their kept-words exist; blocks further back are folded in from global
+//     memory as they are published (they are final long before this block is on the critical path);
+//   * the diagonal block is resolved by one warp, 32 rows at a time, not by a 32-step chain but by
+//     rounds of two ballots: every candidate with no surviving earlier conflicting candidate is
+//     kept at once, everything those rows suppress is dropped (1-2 rounds on video-like data).
 constexpr int kScanRows = 512;
 constexpr int kScanWords = kScanRows / 32;   // 16
 constexpr int kScanThreads = 512;
+constexpr int kScanStride = kScanWords + 1;  // 17: conflict-free rows
+constexpr int kScanPrev = 2;                 // predecessor blocks staged in shared memory
+constexpr size_t kScanSmem = (size_t)(1 + kScanPrev) * kScanRows * kScanStride * sizeof(uint32_t);
+constexpr unsigned long long kKeptTag = 1ull << 32;
 
-__global__ void __launch_bounds__(kScanThreads) greedy_scan_kernel(const uint32_t* __restrict__ mask,
+__device__ __forceinline__ unsigned long long kept_poll(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__global__ void __launch_bounds__(kScanThreads, 2) greedy_scan_kernel(const uint32_t* __restrict__ mask,
                                                                    int64_t words_per_row, int64_t n,
-                                                                   uint32_t* kept /*[ceil(n/32)] padded to blocks*/,
-                                                                   int32_t* ready) {
-  __shared__ uint32_t s_diag[kScanRows][kScanWords + 1];
-  __shared__ uint32_t s_pre[kScanRows];
-  __shared__ int s_avail;
+                                                                   unsigned long long* kept /*[blocks * 16], zeroed*/) {
+  extern __shared__ uint32_t s_scan[];
+  uint32_t* s_diag = s_scan;                                     // [512][17]
+  uint32_t* s_prev = s_scan + kScanRows * kScanStride;           // [2][512][17]: columns of block b-1, b-2
+  __shared__ uint32_t s_kw[kScanPrev][kScanWords];
+  __shared__ uint32_t s_supp[kScanRows];
   const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;   // 16 warps x 32 rows
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;   // 16 warps x 32 rows
   const int64_t r0 = (int64_t)b * kScanRows;
 
-  // diagonal block -> smem (rows beyond n: zero bits, treated as suppressed later)
-  for (int i = threadIdx.x; i < kScanRows * kScanWords; i += kScanThreads) {
+  // diagonal block and the columns of the two preceding blocks -> smem (rows beyond n: zero bits)
+  for (int i = tid; i < kScanRows * kScanWords; i += kScanThreads) {
     const int r = i / kScanWords, w = i - r * kScanWords;
     const int64_t row = r0 + r;
     uint32_t v = 0;
     // words beyond the row's own position were never written by the contraction
-    if (row < n && (int64_t)b * kScanWords + w <= (row >> 5)) v = mask[row * words_per_row + (int64_t)b * kScanWords + w];
-    s_diag[r][w] = v;
+    if (row < n && (int64_t)b * kScanWords + w <= (row >> 5)) v = __ldg(&mask[row * words_per_row + (int64_t)b * kScanWords + w]);
+    s_diag[r * kScanStride + w] = v;
+#pragma unroll
+    for (int pb = 1; pb <= kScanPrev; ++pb) {
+      uint32_t u = 0;
+      if (row < n && b - pb >= 0) u = __ldg(&mask[row * words_per_row + (int64_t)(b - pb) * kScanWords + w]);
+      s_prev[((pb - 1) * kScanRows + r) * kScanStride + w] = u;
+    }
   }
-  uint32_t pre[32 / 1];  // per warp: 32 rows; lane l accumulates for every row, reduced by ballot
+
+  // blocks 0 .. b-3 from global memory: warp = 32 rows, lane = one kept-word of a group of 32
+  uint32_t pre[32];
 #pragma unroll
   for (int r = 0; r < 32; ++r) pre[r] = 0;
-
-  int done = 0;
-  while (done < b) {
-    if (threadIdx.x == 0) {
-      int a;
-      do {
-        a = *((volatile int32_t*)ready);
-      } while (a <= done);
-      s_avail = a < b ? a : b;
-    }
-    __syncthreads();
-    const int avail = s_avail;
-    __threadfence();   // acquire side of the kept-words published before `ready` moved
-    const int64_t wlo = (int64_t)done * kScanWords, whi = (int64_t)avail * kScanWords;
-    for (int64_t w = wlo + lane; w < whi; w += 32) {
-      const uint32_t kw = __ldcg(&kept[w]);
-      if (kw != 0) {
+  const int64_t nbulk = (int64_t)max(b - kScanPrev, 0) * kScanWords;
+  for (int64_t w0 = 0; w0 < nbulk; w0 += 32) {
+    const int64_t w = w0 + lane;
+    const bool in = w < nbulk;
+    unsigned long long v = 0;
+    do {
+      if (in && !(v >> 32)) v = kept_poll(&kept[w]);
+    } while (!__all_sync(0xffffffffu, !in || (v >> 32) != 0));
+    const uint32_t kw = (uint32_t)v;
+    if (kw != 0) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const int64_t row = r0 + wid * 32 + r;
-          if (row < n) pre[r] |= __ldg(&mask[row * words_per_row + w]) & kw;
-        }
+      for (int r = 0; r < 32; ++r) {
+        const int64_t row = r0 + wid * 32 + r;
+        if (row < n) pre[r] |= __ldg(&mask[row * words_per_row + w]) & kw;
       }
     }
-    done = avail;
-    __syncthreads();
   }
+  bool supp = r0 + tid >= n;       // thread = row from here on
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const unsigned any = __ballot_sync(0xffffffffu, pre[r] != 0);
-    if (lane == 0) s_pre[wid * 32 + r] = any;
+    if (lane == r) supp |= any != 0;
+  }
+
+  // the two predecessors: poll their 16 + 16 kept-words (b-2 is published before b-1, waiting for both loses nothing)
+  if (wid == 0) {
+    const int pb = 1 + (lane >> 4), w = lane & 15;
+    uint32_t kw = 0;
+    if (b - pb >= 0) {
+      unsigned long long v;
+      do { v = kept_poll(&kept[(int64_t)(b - pb) * kScanWords + w]); } while (!(v >> 32));
+      kw = (uint32_t)v;
+    }
+    s_kw[pb - 1][w] = kw;
+  }
+  __syncthreads();                 // also orders the smem staging above
+  {
+    uint32_t hit = 0;
+#pragma unroll
+    for (int pb = 0; pb < kScanPrev; ++pb)
+#pragma unroll
+      for (int w = 0; w < kScanWords; ++w) hit |= s_prev[(pb * kScanRows + tid) * kScanStride + w] & s_kw[pb][w];
+    s_supp[tid] = (supp || hit != 0) ? 1u : 0u;
   }
   __syncthreads();
 
   if (wid == 0) {
-    uint32_t keptloc[kScanWords];
+    // lane l carries rows sb * 32 + l of every sub-block; bit sb of supp16 = that row is suppressed
+    uint32_t supp16 = 0;
+#pragma unroll
+    for (int sb = 0; sb < kScanWords; ++sb) supp16 |= s_supp[sb * 32 + lane] << sb;
 #pragma unroll
     for (int sb = 0; sb < kScanWords; ++sb) {
-      const int r = sb * 32 + lane;
-      const int64_t row = r0 + r;
-      bool supp = (row >= n) || (s_pre[r] != 0);
+      // words of the LATER sub-blocks against this one (independent of the outcome: loaded first)
+      uint32_t upd[kScanWords];
 #pragma unroll
-      for (int w = 0; w < kScanWords; ++w)
-        if (w < sb) supp |= (s_diag[r][w] & keptloc[w]) != 0;
-      const uint32_t dw = s_diag[r][sb];
-      const uint32_t suppmask = __ballot_sync(0xffffffffu, supp);
+      for (int s2 = sb + 1; s2 < kScanWords; ++s2) upd[s2] = s_diag[(s2 * 32 + lane) * kScanStride + sb];
+      const uint32_t dw = s_diag[(sb * 32 + lane) * kScanStride + sb];    // bits j < lane only
+      uint32_t cand = __ballot_sync(0xffffffffu, !((supp16 >> sb) & 1u));
       uint32_t km = 0;
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        const uint32_t wl = __shfl_sync(0xffffffffu, dw, l);
-        const bool keep = ((wl & km) == 0) && !((suppmask >> l) & 1u);
-        km |= keep ? (1u << l) : 0u;
+      while (cand) {
+        const bool mine = (cand >> lane) & 1u;
+        const uint32_t keep_now = __ballot_sync(0xffffffffu, mine && (dw & cand) == 0);   // never empty: the lowest candidate
+        km |= keep_now;
+        const uint32_t killed = __ballot_sync(0xffffffffu, mine && (dw & keep_now) != 0);
+        cand &= ~(keep_now | killed);
       }
-      keptloc[sb] = km;
-      if (lane == 0) kept[(int64_t)b * kScanWords + sb] = km;
+      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&kept[(int64_t)b * kScanWords + sb]) = kKeptTag | km;
+#pragma unroll
+      for (int s2 = sb + 1; s2 < kScanWords; ++s2) supp16 |= ((upd[s2] & km) != 0 ? 1u : 0u) << s2;
     }
-    __threadfence();
-    if (lane == 0) atomicExch(ready, b + 1);
   }
 }
 
 // ---- 5. kept bitmap -> ascending row numbers ---------------------------------------------
-__global__ void __launch_bounds__(1024) compact_kernel(const uint32_t* __restrict__ kept, int64_t nwords,
+__global__ void __launch_bounds__(1024) compact_kernel(const unsigned long long* __restrict__ kept, int64_t nwords,
                                                        int64_t n, int64_t* __restrict__ out_keep,
                                                        int32_t* __restrict__ out_count) {
   __shared__ int64_t s_sum[1024];
@@ -152,7 +190,7 @@ __global__ void __launch_bounds__(1024) compact_kernel(const uint32_t* __restric
   const int64_t per = (nwords + 1023) / 1024;
   const int64_t w0 = t * per, w1 = min(w0 + per, nwords);
   int64_t c = 0;
-  for (int64_t w = w0; w < w1; ++w) c += __popc(kept[w]);
+  for (int64_t w = w0; w < w1; ++w) c += __popc((uint32_t)kept[w]);
   s_sum[t] = c;
   __syncthreads();
   // inclusive scan (Hillis-Steele; 1024 entries, one launch per consolidation)
@@ -164,7 +202,7 @@ __global__ void __launch_bounds__(1024) compact_kernel(const uint32_t* __restric
   }
   int64_t pos = s_sum[t] - c;
   for (int64_t w = w0; w < w1; ++w) {
-    uint32_t bits = kept[w];
+    uint32_t bits = (uint32_t)kept[w];   // low half of the tagged word
     while (bits) {
       const int bpos = __ffs(bits) - 1;
       bits &= bits - 1;
@@ -193,7 +231,7 @@ struct ConsLayout {
   float* norm;
   uint32_t* mask;
   int64_t words_per_row;
-  uint32_t* kept;
+  unsigned long long* kept;   // tagged kept-words (greedy_scan_kernel)
   int64_t kept_words;
   uint2* unc;
   int32_t unc_cap;
@@ -209,7 +247,7 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d) {
   L.words_per_row = (n + kTcBN - 1) / kTcBN * (kTcBN / 32);
   L.mask = c.take<uint32_t>((size_t)n * L.words_per_row);
   L.kept_words = (n + kScanRows - 1) / kScanRows * kScanWords;
-  L.kept = c.take<uint32_t>((size_t)L.kept_words);
+  L.kept = c.take<unsigned long long>((size_t)L.kept_words);
   int64_t cap = 64 * n + (1 << 20);
   if (cap > 0x3fffffff) cap = 0x3fffffff;
   L.unc_cap = (int32_t)cap;
@@ -274,7 +312,9 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
                                                  L.mask, L.words_per_row);
   HIPPO_CUDA(cudaGetLastError());
   const int scan_blocks = (int)((n + kScanRows - 1) / kScanRows);
-  greedy_scan_kernel<<<scan_blocks, kScanThreads, 0, s>>>(L.mask, L.words_per_row, n, L.kept, L.counters + 1);
+  HIPPO_CUDA(cudaMemsetAsync(L.kept, 0, (size_t)L.kept_words * sizeof(unsigned long long), s));
+  HIPPO_CUDA(cudaFuncSetAttribute(greedy_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+  greedy_scan_kernel<<<scan_blocks, kScanThreads, kScanSmem, s>>>(L.mask, L.words_per_row, n, L.kept);
   HIPPO_CUDA(cudaGetLastError());
   compact_kernel<<<1, 1024, 0, s>>>(L.kept, L.kept_words, n, out_keep, out_count);
   HIPPO_CUDA(cudaGetLastError());

@@ -126,3 +126,41 @@ def test_greedy_invariant_100k(cuda_device):
             assert best < 0.9 + 1e-3, f"kept row {lo + r} has a kept predecessor at {best}"
         else:
             assert best >= 0.9 - 1e-3, f"dropped row {lo + r} but best kept predecessor is {best}"
+
+
+@pytest.mark.parametrize("kind", ["chain", "all_kept", "all_dropped"])
+def test_scan_adversarial_structures(cuda_device, kind):
+    """Shapes of the conflict graph that stress the block-to-block chain and the ballot rounds of the
+    in-block resolution: a walk where every row conflicts with its predecessor only (keep, drop, keep, ...:
+    one ballot round per kept row), independent rows (everything kept) and one tight cluster (only row 0)."""
+    from hippomm_b200 import select_key_frames
+
+    rng = np.random.default_rng(77)
+    n, d = 2100, 1024
+    if kind == "chain":
+        c, s = 0.93, np.sqrt(1 - 0.93 ** 2)   # sim(i, i+1) = .93 >= gamma, sim(i, i+2) ~ .865 < gamma
+        v = rng.standard_normal(d)
+        v /= np.linalg.norm(v)
+        rows = []
+        for _ in range(n):
+            rows.append(v.copy())
+            u = rng.standard_normal(d)
+            u -= u.dot(v) * v
+            u /= np.linalg.norm(u)
+            v = c * v + s * u
+        feats = np.asarray(rows, dtype=np.float32) * 3.0
+    elif kind == "all_kept":
+        feats = rng.standard_normal((n, d)).astype(np.float32)
+    else:
+        base = rng.standard_normal(d).astype(np.float32)
+        feats = base[None, :] + 0.01 * rng.standard_normal((n, d)).astype(np.float32)
+    ref, moat = O.select_key_frames_blocked(feats, 0.9, block=700, with_moat=True)
+    kept = select_key_frames(feats, None, 0.9)
+    assert moat > 1e-6, moat
+    assert np.array_equal(kept, ref), f"{kind}: {len(kept)} kept vs {len(ref)}"
+    if kind == "chain":
+        assert len(ref) > n // 3
+    elif kind == "all_kept":
+        assert len(ref) == n
+    else:
+        assert list(ref) == [0]
