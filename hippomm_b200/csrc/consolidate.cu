@@ -10,6 +10,9 @@
 // matrix is N^2/8 bytes.
 #include "common.cuh"
 #include "sim_tc.cuh"
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
 
 namespace hippo {
 
@@ -52,132 +55,176 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
 }
 
 // ---- 4. greedy scan over the bit matrix ------------------------------------------------
-// CTA b owns rows [512 b, 512 b + 512).  The chain over blocks is sequential (a row's fate depends on
-// which earlier rows were KEPT), so the kernel is bound by the hand-off latency between consecutive
-// blocks; everything that does not depend on the predecessor's result is done ahead of it:
+// CTA b owns rows [512 b, 512 b + 512), one thread per row.  The chain over blocks is sequential (a row's
+// fate depends on which earlier rows were KEPT), so the kernel is bound by the hand-off latency between
+// consecutive blocks; everything that does not depend on the predecessors' results is done ahead of them:
 //   * kept-words are published as self-validating 64-bit values (tag << 32 | word), so a consumer polls
-//     the data itself -- one L2 round trip per hand-off, no separate flag, no fence;
-//   * the mask columns of the two preceding blocks and the 512 x 512 diagonal block are staged in
-//     shared memory before their kept-words exist; blocks further back are folded in from global
-//     memory as they are published (they are final long before this block is on the critical path);
-//   * the diagonal block is resolved by one warp, 32 rows at a time, not by a 32-step chain but by
-//     rounds of two ballots: every candidate with no surviving earlier conflicting candidate is
-//     kept at once, everything those rows suppress is dropped (1-2 rounds on video-like data).
+//     the data itself -- one L2 round trip per hand-off, no separate flag, no fence.  One warp per CTA
+//     polls, and CTAs far behind the frontier sleep between polls: a line hammered by every waiting warp
+//     of the grid delayed the publisher's store by ~5 us (profiles/);
+//   * a thread holds its row's mask words against the block itself and its three predecessors in
+//     registers; blocks further back are folded in from global memory as they are published (they are
+//     final well before this block is on the critical path);
+//   * the 512 x 512 diagonal block is resolved in ROUNDS over the whole block instead of a 512-step chain:
+//     an undecided row is dropped as soon as a conflicting earlier row is known kept, and kept as soon as no
+//     conflicting earlier row is still undecided (depth of the conflict chains, ~two rounds per kept row
+//     of a scene on video-like data, one barrier per round);
+//   * rows with no conflict bit against the three predecessors are resolved (phase A) BEFORE those
+//     predecessors publish; only the rest -- typically the scene straddling the block boundary -- is
+//     left for the critical path (phase B).
 constexpr int kScanRows = 512;
 constexpr int kScanWords = kScanRows / 32;   // 16
-constexpr int kScanThreads = 512;
-constexpr int kScanStride = kScanWords + 1;  // 17: conflict-free rows
-constexpr int kScanPrev = 2;                 // predecessor blocks staged in shared memory
-constexpr size_t kScanSmem = (size_t)(1 + kScanPrev) * kScanRows * kScanStride * sizeof(uint32_t);
+constexpr int kScanThreads = kScanRows;
+constexpr int kScanPreds = 3;
 constexpr unsigned long long kKeptTag = 1ull << 32;
 
 __device__ __forceinline__ unsigned long long kept_poll(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
+// the 16 mask words of `row` against the columns of 512-row block `blk` (64 contiguous bytes)
+__device__ __forceinline__ void load_row_words(const uint32_t* __restrict__ mask, int64_t words_per_row,
+                                               int64_t row, int blk, uint32_t (&out)[kScanWords]) {
+  const uint4* p = reinterpret_cast<const uint4*>(mask + row * words_per_row + (int64_t)blk * kScanWords);
+#pragma unroll
+  for (int i = 0; i < kScanWords / 4; ++i) {
+    const uint4 v = __ldg(p + i);
+    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+  }
+}
+// OR over w of (words[w] & set[w]) for 16 words of shared memory
+__device__ __forceinline__ uint32_t and_any16(const uint32_t (&words)[kScanWords], const uint32_t* set, int nquads) {
+  uint32_t h = 0;
+#pragma unroll
+  for (int i = 0; i < kScanWords / 4; ++i) {
+    if (i < nquads) {
+      const uint4 q = *reinterpret_cast<const uint4*>(set + 4 * i);
+      h |= (words[4 * i] & q.x) | (words[4 * i + 1] & q.y) | (words[4 * i + 2] & q.z) | (words[4 * i + 3] & q.w);
+    }
+  }
+  return h;
+}
 
-__global__ void __launch_bounds__(kScanThreads, 2) greedy_scan_kernel(const uint32_t* __restrict__ mask,
-                                                                   int64_t words_per_row, int64_t n,
-                                                                   unsigned long long* kept /*[blocks * 16], zeroed*/) {
-  extern __shared__ uint32_t s_scan[];
-  uint32_t* s_diag = s_scan;                                     // [512][17]
-  uint32_t* s_prev = s_scan + kScanRows * kScanStride;           // [2][512][17]: columns of block b-1, b-2
-  __shared__ uint32_t s_kw[kScanPrev][kScanWords];
-  __shared__ uint32_t s_supp[kScanRows];
+__global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint32_t* __restrict__ mask,
+                                                                      int64_t words_per_row, int64_t n,
+                                                                      unsigned long long* kept /*[blocks * 16], zeroed*/,
+                                                                      unsigned long long* dbg) {
+  __shared__ __align__(16) uint32_t s_kept[2][kScanWords];
+  __shared__ __align__(16) uint32_t s_undec[2][kScanWords];
+  __shared__ __align__(16) uint32_t s_kw[2][kScanWords];            // bulk ring
+  __shared__ __align__(16) uint32_t s_pk[kScanPreds][kScanWords];   // predecessors' kept-words
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;   // 16 warps x 32 rows
-  const int64_t r0 = (int64_t)b * kScanRows;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t row = (int64_t)b * kScanRows + tid;
+  const bool live = row < n;
+  auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  if (dbg && tid == 0) dbg[b * 8 + 0] = now();
 
-  // diagonal block and the columns of the two preceding blocks -> smem (rows beyond n: zero bits)
-  for (int i = tid; i < kScanRows * kScanWords; i += kScanThreads) {
-    const int r = i / kScanWords, w = i - r * kScanWords;
-    const int64_t row = r0 + r;
-    uint32_t v = 0;
-    // words beyond the row's own position were never written by the contraction
-    if (row < n && (int64_t)b * kScanWords + w <= (row >> 5)) v = __ldg(&mask[row * words_per_row + (int64_t)b * kScanWords + w]);
-    s_diag[r * kScanStride + w] = v;
+  // this row against its own block (bits j < row only; later words were never written) and the three before
+  uint32_t dg[kScanWords], pp[kScanPreds][kScanWords];
 #pragma unroll
-    for (int pb = 1; pb <= kScanPrev; ++pb) {
-      uint32_t u = 0;
-      if (row < n && b - pb >= 0) u = __ldg(&mask[row * words_per_row + (int64_t)(b - pb) * kScanWords + w]);
-      s_prev[((pb - 1) * kScanRows + r) * kScanStride + w] = u;
+  for (int w = 0; w < kScanWords; ++w) {
+    dg[w] = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPreds; ++j) pp[j][w] = 0;
+  }
+  if (live) {
+    load_row_words(mask, words_per_row, row, b, dg);
+#pragma unroll
+    for (int w = 0; w < kScanWords; ++w) {
+      if (w > wid) dg[w] = 0;
+      else if (w == wid) dg[w] &= (1u << lane) - 1u;
     }
+#pragma unroll
+    for (int j = 0; j < kScanPreds; ++j)
+      if (b - 1 - j >= 0) load_row_words(mask, words_per_row, row, b - 1 - j, pp[j]);
   }
+  uint32_t ext = 0;
+#pragma unroll
+  for (int w = 0; w < kScanWords; ++w)
+#pragma unroll
+    for (int j = 0; j < kScanPreds; ++j) ext |= pp[j][w];
+  bool blocked = ext != 0;          // depends on a predecessor that has not published yet
 
-  // blocks 0 .. b-3 from global memory: warp = 32 rows, lane = one kept-word of a group of 32
-  uint32_t pre[32];
+  // blocks 0 .. b-4 from global memory, one block (16 kept-words) per step; warp 0 polls
+  uint32_t hit = 0;
+  const int nbulk = max(b - kScanPreds, 0);
+  for (int g = 0; g < nbulk; ++g) {
+    uint4 m[4];
 #pragma unroll
-  for (int r = 0; r < 32; ++r) pre[r] = 0;
-  const int64_t nbulk = (int64_t)max(b - kScanPrev, 0) * kScanWords;
-  for (int64_t w0 = 0; w0 < nbulk; w0 += 32) {
-    const int64_t w = w0 + lane;
-    const bool in = w < nbulk;
-    unsigned long long v = 0;
-    do {
-      if (in && !(v >> 32)) v = kept_poll(&kept[w]);
-    } while (!__all_sync(0xffffffffu, !in || (v >> 32) != 0));
-    const uint32_t kw = (uint32_t)v;
-    if (kw != 0) {
+    for (int i = 0; i < 4; ++i) m[i] = make_uint4(0, 0, 0, 0);
+    if (live) {
+      const uint4* p = reinterpret_cast<const uint4*>(mask + row * words_per_row + (int64_t)g * kScanWords);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const int64_t row = r0 + wid * 32 + r;
-        if (row < n) pre[r] |= __ldg(&mask[row * words_per_row + w]) & kw;
-      }
+      for (int i = 0; i < 4; ++i) m[i] = __ldg(p + i);
     }
-  }
-  bool supp = r0 + tid >= n;       // thread = row from here on
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const unsigned any = __ballot_sync(0xffffffffu, pre[r] != 0);
-    if (lane == r) supp |= any != 0;
-  }
-
-  // the two predecessors: poll their 16 + 16 kept-words (b-2 is published before b-1, waiting for both loses nothing)
-  if (wid == 0) {
-    const int pb = 1 + (lane >> 4), w = lane & 15;
-    uint32_t kw = 0;
-    if (b - pb >= 0) {
+    if (wid == 0 && lane < kScanWords) {
       unsigned long long v;
-      do { v = kept_poll(&kept[(int64_t)(b - pb) * kScanWords + w]); } while (!(v >> 32));
-      kw = (uint32_t)v;
+      while (!((v = kept_poll(&kept[(int64_t)g * kScanWords + lane])) >> 32))
+        if (b - g > 6) __nanosleep(2000);
+      s_kw[g & 1][lane] = (uint32_t)v;
     }
-    s_kw[pb - 1][w] = kw;
-  }
-  __syncthreads();                 // also orders the smem staging above
-  {
-    uint32_t hit = 0;
+    __syncthreads();
+    const uint32_t* kw = s_kw[g & 1];
 #pragma unroll
-    for (int pb = 0; pb < kScanPrev; ++pb)
-#pragma unroll
-      for (int w = 0; w < kScanWords; ++w) hit |= s_prev[(pb * kScanRows + tid) * kScanStride + w] & s_kw[pb][w];
-    s_supp[tid] = (supp || hit != 0) ? 1u : 0u;
+    for (int i = 0; i < 4; ++i) {
+      const uint4 q = *reinterpret_cast<const uint4*>(kw + 4 * i);
+      hit |= (m[i].x & q.x) | (m[i].y & q.y) | (m[i].z & q.z) | (m[i].w & q.w);
+    }
   }
-  __syncthreads();
+  if (dbg && tid == 0) dbg[b * 8 + 1] = now();
 
-  if (wid == 0) {
-    // lane l carries rows sb * 32 + l of every sub-block; bit sb of supp16 = that row is suppressed
-    uint32_t supp16 = 0;
-#pragma unroll
-    for (int sb = 0; sb < kScanWords; ++sb) supp16 |= s_supp[sb * 32 + lane] << sb;
-#pragma unroll
-    for (int sb = 0; sb < kScanWords; ++sb) {
-      // words of the LATER sub-blocks against this one (independent of the outcome: loaded first)
-      uint32_t upd[kScanWords];
-#pragma unroll
-      for (int s2 = sb + 1; s2 < kScanWords; ++s2) upd[s2] = s_diag[(s2 * 32 + lane) * kScanStride + sb];
-      const uint32_t dw = s_diag[(sb * 32 + lane) * kScanStride + sb];    // bits j < lane only
-      uint32_t cand = __ballot_sync(0xffffffffu, !((supp16 >> sb) & 1u));
-      uint32_t km = 0;
-      while (cand) {
-        const bool mine = (cand >> lane) & 1u;
-        const uint32_t keep_now = __ballot_sync(0xffffffffu, mine && (dw & cand) == 0);   // never empty: the lowest candidate
-        km |= keep_now;
-        const uint32_t killed = __ballot_sync(0xffffffffu, mine && (dw & keep_now) != 0);
-        cand &= ~(keep_now | killed);
+  bool undec = live && hit == 0;
+  bool kept_me = false;
+  int round = 0;
+  const int nquads = wid / 4 + 1;     // dg words beyond the row's own are zero
+  // rounds until nothing changes; blocked rows stay undecided (and count as such for the others)
+  auto run_rounds = [&]() {
+    bool changed = true;
+    for (;; ++round) {
+      const int buf = round & 1;
+      const uint32_t uw = __ballot_sync(0xffffffffu, undec);
+      const uint32_t kwd = __ballot_sync(0xffffffffu, kept_me);
+      if (lane == 0) { s_undec[buf][wid] = uw; s_kept[buf][wid] = kwd; }
+      if (!__syncthreads_or(changed ? 1 : 0)) break;     // barrier + "did the last round decide anything?"
+      changed = false;
+      if (undec && !blocked) {
+        if (and_any16(dg, s_kept[buf], nquads) != 0) { undec = false; changed = true; }              // a conflicting earlier row is kept
+        else if (and_any16(dg, s_undec[buf], nquads) == 0) { undec = false; kept_me = true; changed = true; }  // none can still be kept
       }
-      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&kept[(int64_t)b * kScanWords + sb]) = kKeptTag | km;
-#pragma unroll
-      for (int s2 = sb + 1; s2 < kScanWords; ++s2) supp16 |= ((upd[s2] & km) != 0 ? 1u : 0u) << s2;
     }
+    ++round;   // the buffer written last stays intact for the next call's first barrier
+  };
+  run_rounds();                                       // phase A
+  if (dbg && tid == 0) { dbg[b * 8 + 5] = now(); dbg[b * 8 + 6] = round; }
+
+  // phase B: the three predecessors' kept-words (b-3 and b-2 by warp 0, b-1 by warp 1)
+  if (b >= 1) {
+    if (wid < 2) {
+      const int j = wid == 0 ? 2 - (lane >> 4) : 0;   // predecessor b-1-j
+      if ((wid == 0 || lane < kScanWords) && b - 1 - j >= 0) {
+        unsigned long long v;
+        while (!((v = kept_poll(&kept[(int64_t)(b - 1 - j) * kScanWords + (lane & 15)])) >> 32)) {}
+        s_pk[j][lane & 15] = (uint32_t)v;
+      } else if (wid == 0 || lane < kScanWords) {
+        s_pk[j][lane & 15] = 0;
+      }
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[b * 8 + 2] = now();
+    if (blocked) {
+      uint32_t h = 0;
+#pragma unroll
+      for (int j = 0; j < kScanPreds; ++j) h |= and_any16(pp[j], s_pk[j], 4);
+      if (h != 0) undec = false;
+      blocked = false;
+    }
+    run_rounds();
+  } else if (dbg && tid == 0) dbg[b * 8 + 2] = now();
+
+  {
+    const uint32_t kwd = __ballot_sync(0xffffffffu, kept_me);
+    if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&kept[(int64_t)b * kScanWords + wid]) = kKeptTag | kwd;
+    if (dbg && tid == 0) { dbg[b * 8 + 3] = now(); dbg[b * 8 + 4] = round; }
   }
 }
 
@@ -313,8 +360,21 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
   HIPPO_CUDA(cudaGetLastError());
   const int scan_blocks = (int)((n + kScanRows - 1) / kScanRows);
   HIPPO_CUDA(cudaMemsetAsync(L.kept, 0, (size_t)L.kept_words * sizeof(unsigned long long), s));
-  HIPPO_CUDA(cudaFuncSetAttribute(greedy_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
-  greedy_scan_kernel<<<scan_blocks, kScanThreads, kScanSmem, s>>>(L.mask, L.words_per_row, n, L.kept);
+  unsigned long long* dbg = nullptr;
+  if (getenv("HIPPO_SCAN_DEBUG")) cudaMalloc(&dbg, (size_t)scan_blocks * 64);
+  greedy_scan_kernel<<<scan_blocks, kScanThreads, 0, s>>>(L.mask, L.words_per_row, n, L.kept, dbg);
+  if (dbg) {
+    cudaStreamSynchronize(s);
+    std::vector<unsigned long long> h((size_t)scan_blocks * 8);
+    cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    const unsigned long long t0 = h[0];
+    for (int i = 0; i < scan_blocks; ++i)
+      if (i < 6 || i % 16 == 0 || i > scan_blocks - 4)
+        fprintf(stderr, "[scan] blk %3d start %8.2f bulk_done %8.2f phaseA %8.2f (%llu rounds) preds %8.2f published %8.2f us  (rounds %llu, since prev publish %.2f)\n", i,
+                (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 5] - t0) / 1e3, h[i * 8 + 6], (h[i * 8 + 2] - t0) / 1e3, (h[i * 8 + 3] - t0) / 1e3, h[i * 8 + 4],
+                i ? (h[i * 8 + 3] - h[(i - 1) * 8 + 3]) / 1e3 : 0.0);
+  }
   HIPPO_CUDA(cudaGetLastError());
   compact_kernel<<<1, 1024, 0, s>>>(L.kept, L.kept_words, n, out_keep, out_count);
   HIPPO_CUDA(cudaGetLastError());

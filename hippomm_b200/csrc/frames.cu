@@ -25,43 +25,58 @@ __device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r)
   return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
 }
 
-// grid (blocks_per_frame, nf)
+// grid (blocks_per_frame, nf).  3-channel fast path: a warp takes 32 groups of 16 pixels per step = 1536
+// contiguous BGR bytes, loaded as three fully coalesced 512-byte rows into the warp's shared-memory slot, then
+// every lane picks up its own 48 bytes (conflict-free: 12-word stride) and stores 16 gray bytes, coalesced.
 __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restrict__ frames, int64_t npix,
                                                           int ch, uint8_t* __restrict__ gray,
                                                           int2* __restrict__ minmax) {
+  __shared__ uint4 s_stage[8][96];
+  __shared__ uint32_t s_lo[8], s_hi[8];
   const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint8_t* src = frames + (int64_t)f * npix * ch;
   uint8_t* dst = gray + (int64_t)f * npix;
   uint32_t lo = 255, hi = 0;
   const bool vec = (npix % 16 == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0);
   if (ch == 3 && vec) {
-    // 16 pixels = 48 BGR bytes = three 128-bit loads -> one 128-bit store
     const int64_t ngroups = npix / 16;
-    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
-         gi += (int64_t)gridDim.x * blockDim.x) {
-      const uint4* p = reinterpret_cast<const uint4*>(src + gi * 48);
-      const uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = ldg_stream(p + 2);
-      const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-      uint32_t out[4];
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t g0 = ((int64_t)blockIdx.x * 8 + warp) * 32; g0 < ngroups; g0 += nwarps * 32) {
+      const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
+      const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
+      const uint4* p = reinterpret_cast<const uint4*>(src + g0 * 48);
+      uint4 v[3];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        uint32_t packed = 0;
+      for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) v[u] = ldg_stream(p + lane + 32 * u);
 #pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          const int byte0 = (o * 4 + px) * 3;
-          uint32_t v[3];
+      for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
+      __syncwarp();
+      if (lane < left) {
+        const uint4 a = s_stage[warp][3 * lane], b = s_stage[warp][3 * lane + 1], c = s_stage[warp][3 * lane + 2];
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t out[4];
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) {
-            const int bi = byte0 + cc;
-            v[cc] = (w[bi >> 2] >> ((bi & 3) * 8)) & 0xffu;
+        for (int o = 0; o < 4; ++o) {
+          uint32_t packed = 0;
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const int byte0 = (o * 4 + px) * 3;
+            uint32_t c3[3];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              const int bi = byte0 + cc;
+              c3[cc] = (w[bi >> 2] >> ((bi & 3) * 8)) & 0xffu;
+            }
+            const uint32_t y = bgr2gray(c3[0], c3[1], c3[2]);
+            lo = min(lo, y); hi = max(hi, y);
+            packed |= y << (px * 8);
           }
-          const uint32_t y = bgr2gray(v[0], v[1], v[2]);
-          lo = min(lo, y); hi = max(hi, y);
-          packed |= y << (px * 8);
+          out[o] = packed;
         }
-        out[o] = packed;
+        *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
       }
-      *reinterpret_cast<uint4*>(dst + gi * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+      __syncwarp();
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
@@ -78,7 +93,11 @@ __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restr
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { lo = min(lo, s_lo[i]); hi = max(hi, s_hi[i]); }
     atomicMin(&minmax[f].x, (int)lo);
     atomicMax(&minmax[f].y, (int)hi);
   }
