@@ -12,11 +12,14 @@
 // cancellation error, and only the final ratio is evaluated in fp32.
 //
 //   gray_minmax_kernel : BGR -> gray (cv2's fixed point: (3735 B + 19235 G + 9798 R + 16384) >> 15),
-//                        per-frame min / max (the data range of hm:990 is computed in uint8)
-//   ssim_pair_kernel   : one CTA per (pair, band of rows); threads own columns, march down the
-//                        rows with sliding 7-row column sums, exchange them through shared memory
-//                        for the 7-column horizontal sum
-//   ssim_finalize_kernel: ordered sum of the band partials -> mean SSIM, MSE
+//                        rows padded with zeros to a multiple of 4 bytes, per-frame min / max (the data
+//                        range of hm:990 is computed in uint8)
+//   ssim_pair_kernel   : one WARP per (pair, band of rows, chunk of 120 columns), no block-level
+//                        synchronisation.  A lane owns 4 adjacent columns (one 32-bit word of each frame
+//                        per row), marches down the rows with sliding 7-row column sums, and gets the
+//                        6 columns to its right from its two neighbours with 16 shuffles of column-sum
+//                        prefixes.  Issue-bound (integer ALU), not HBM-bound: see DESIGN.md.
+//   ssim_finalize_kernel: ordered sum of the warp partials -> mean SSIM, MSE
 #include "common.cuh"
 
 namespace hippo {
@@ -29,16 +32,17 @@ __device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r)
 // contiguous BGR bytes, loaded as three fully coalesced 512-byte rows into the warp's shared-memory slot, then
 // every lane picks up its own 48 bytes (conflict-free: 12-word stride) and stores 16 gray bytes, coalesced.
 __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restrict__ frames, int64_t npix,
-                                                          int ch, uint8_t* __restrict__ gray,
+                                                          int w, int pitch, int ch, uint8_t* __restrict__ gray,
                                                           int2* __restrict__ minmax) {
   __shared__ uint4 s_stage[8][96];
   __shared__ uint32_t s_lo[8], s_hi[8];
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint8_t* src = frames + (int64_t)f * npix * ch;
-  uint8_t* dst = gray + (int64_t)f * npix;
+  const int64_t gpix = npix / w * pitch;      // bytes of one padded gray frame
+  uint8_t* dst = gray + (int64_t)f * gpix;
   uint32_t lo = 255, hi = 0;
-  const bool vec = (npix % 16 == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0);
+  const bool vec = pitch == w && (npix % 16 == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0);
   if (ch == 3 && vec) {
     const int64_t ngroups = npix / 16;
     const int64_t nwarps = (int64_t)gridDim.x * 8;
@@ -79,12 +83,16 @@ __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restr
       __syncwarp();
     }
   } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < gpix;
+         o += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = o / pitch;
+      const int x = (int)(o - r * pitch);
+      if (x >= w) { dst[o] = 0; continue; }   // row padding: zero in both frames of a pair
+      const int64_t i = r * w + x;
       uint32_t y;
       if (ch == 3) y = bgr2gray(src[i * 3], src[i * 3 + 1], src[i * 3 + 2]);
       else y = src[i];
-      dst[i] = (uint8_t)y;
+      dst[o] = (uint8_t)y;
       lo = min(lo, y); hi = max(hi, y);
     }
   }
@@ -109,24 +117,33 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 }
 
 constexpr int kSsimThreads = 256;
-constexpr int kSsimChunk = kSsimThreads - 6;   // output columns per column chunk
+constexpr int kSsimWarps = kSsimThreads / 32;
+constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
+constexpr int kSsimBand = 56;                  // window rows per band
 
-// grid (nbands, npairs).  Band k produces SSIM rows [k*bh, min((k+1)*bh, h-6)) (window top rows)
-// and the squared-error sum of image rows [k*bh, ...) (last band: through h).
-__global__ void __launch_bounds__(kSsimThreads) ssim_pair_kernel(
-    const uint8_t* __restrict__ gray, int h, int w, const int32_t* __restrict__ pair_a,
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 | k); }
+
+// One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
+// squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
+// [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
+__global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
+    const uint8_t* __restrict__ gray, int h, int w, int pitch, const int32_t* __restrict__ pair_a,
     const int32_t* __restrict__ pair_b, const int2* __restrict__ minmax, int range_mode, int bh,
-    int nbands, double* __restrict__ part_ssim, unsigned long long* __restrict__ part_sse) {
-  __shared__ int4 s_cs[2][kSsimThreads];
-  __shared__ double s_red[kSsimThreads / 32];
-  __shared__ unsigned long long s_red2[kSsimThreads / 32];
-
-  const int band = blockIdx.x, p = blockIdx.y;
+    int nbands, int nchunks, int64_t nitems, double* __restrict__ part_ssim,
+    unsigned long long* __restrict__ part_sse) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
+  if (item >= nitems) return;
+  const int chunk = (int)(item % nchunks);
+  const int band = (int)((item / nchunks) % nbands);
+  const int p = (int)(item / ((int64_t)nchunks * nbands));
   const int fa = pair_a ? pair_a[p] : p + 1;
   const int fb = pair_b ? pair_b[p] : p;
-  const int64_t npix = (int64_t)h * w;
-  const uint8_t* ga = gray + (int64_t)fa * npix;
-  const uint8_t* gb = gray + (int64_t)fb * npix;
+  const int64_t gpix = (int64_t)h * pitch;
+  const int wordx = (chunk * 30 + lane) * 4;                 // byte offset of this lane's word in a row
+  const bool col_ok = wordx < pitch;
+  const uint8_t* ga = gray + (int64_t)fa * gpix + wordx;
+  const uint8_t* gb = gray + (int64_t)fb * gpix + wordx;
 
   // data range: hm:990 takes max - min of the FIRST frame in uint8; bp:61 fixes it at 1.0 on
   // the /255 scale, i.e. 255 on the integer scale
@@ -139,74 +156,90 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_pair_kernel(
   const int out_rows = h - 6, out_cols = w - 6;
   const int y0 = band * bh;
   const int y1 = min(y0 + bh, out_rows);          // window-top rows [y0, y1)
-  const int t = threadIdx.x;
+  const int rows_in = (y1 > y0) ? (y1 - y0 + 6) : 0;
+  const int sse_r1 = (band == nbands - 1) ? h : min(y0 + bh, h);
+  const int rend = max(y0 + rows_in, sse_r1);
+  // every image word is counted for the squared error by exactly one warp: chunks overlap by two words
+  const bool sse_own = col_ok && (lane < 30 || chunk == nchunks - 1);
+  // which of this lane's four windows exist and belong to this chunk
+  bool own[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) own[k] = lane < 30 && chunk * kSsimChunk + lane * 4 + k < out_cols;
+
+  int sp[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
   double acc = 0.0;
   unsigned long long sse = 0;
-  const int sse_r1 = (band == nbands - 1) ? h : min(y0 + bh, h);
+  uint32_t sq = 0, cr = 0;                        // sum a^2 + b^2, sum a b of the rows owned for the squared error
 
-  for (int cb = 0; cb < max(out_cols, 1); cb += kSsimChunk) {
-    const int x = cb + t;                         // input column of this thread
-    const bool col_ok = x < w;
-    // every image column is counted for the squared error by exactly one chunk (chunks overlap
-    // by 6 columns): a chunk owns its first 250 columns, the last chunk owns all of its columns
-    const bool sse_col = col_ok && (t < kSsimChunk || cb + kSsimChunk >= out_cols);
-    int sxy_p = 0, sxx = 0, syy = 0, sxy = 0;     // sliding 7-row column sums (sx | sy << 16 packed)
-    const int rows_in = (y1 > y0) ? (y1 - y0 + 6) : 0;
-    const int rend = max(y0 + rows_in, sse_r1);
-    for (int r = y0; r < rend; ++r) {
-      int xa = 0, xb = 0;
-      if (col_ok && r < h) { xa = __ldg(ga + (int64_t)r * w + x); xb = __ldg(gb + (int64_t)r * w + x); }
-      if (sse_col && r < sse_r1) {
-        const int dlt = xa - xb;
-        sse += (unsigned long long)(dlt * dlt);
-      }
-      if (r >= y0 + rows_in) continue;            // rows only needed for the squared error (uniform)
-      sxy_p += xa | (xb << 16);
-      sxx += xa * xa; syy += xb * xb; sxy += xa * xb;
-      if (r >= y0 + 7) {
-        int oa = 0, ob = 0;
-        if (col_ok) { oa = __ldg(ga + (int64_t)(r - 7) * w + x); ob = __ldg(gb + (int64_t)(r - 7) * w + x); }
-        sxy_p -= oa | (ob << 16);
-        sxx -= oa * oa; syy -= ob * ob; sxy -= oa * ob;
+  auto ldw = [&](const uint8_t* g, int r) -> uint32_t {
+    return (col_ok && r >= y0 && r < h) ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
+  };
+  uint32_t wa = ldw(ga, y0), wb = ldw(gb, y0), oa = 0, ob = 0;
+  for (int r = y0; r < rend; ++r) {
+    // next row's words: issued now, used in the next iteration
+    const uint32_t nwa = ldw(ga, r + 1), nwb = ldw(gb, r + 1);
+    const uint32_t noa = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(ga, r - 6) : 0u;
+    const uint32_t nob = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(gb, r - 6) : 0u;
+    if (sse_own && r < sse_r1) {
+      sq = __dp4a(wa, wa, sq); sq = __dp4a(wb, wb, sq); cr = __dp4a(wa, wb, cr);
+      if ((r & 63) == 63) { sse += (unsigned long long)sq - 2ull * cr; sq = 0; cr = 0; }   // 64 rows x 8 x 255^2 < 2^32
+    }
+    if (r < y0 + rows_in) {                       // warp-uniform
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int an = (int)byte_of(wa, k), bn = (int)byte_of(wb, k);
+        const int ao = (int)byte_of(oa, k), bo = (int)byte_of(ob, k);
+        const int da = an - ao, db = bn - bo;
+        sp[k] += da + db * 65536;                 // sum x | sum y << 16: the running sums never go negative
+        sxx[k] += da * (an + ao);
+        syy[k] += db * (bn + bo);
+        sxy[k] += an * bn - ao * bo;
       }
       if (r >= y0 + 6) {
-        const int buf = r & 1;
-        s_cs[buf][t] = make_int4(sxy_p, sxx, syy, sxy);
-        __syncthreads();
-        // thread t produces the window whose left column is cb + t
-        if (t < kSsimChunk && cb + t < out_cols) {
-          int4 s = s_cs[buf][t];
+        // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
+        // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
+        float s4 = 0.f;
+        int o_sp[4], o_xx[4], o_yy[4], o_xy[4];
+        auto horiz = [&](const int (&c)[4], int (&o)[4]) {
+          const int A = c[0], B = A + c[1], C = B + c[2], D = C + c[3];
+          const int C1n = __shfl_down_sync(0xffffffffu, C, 1), D1n = __shfl_down_sync(0xffffffffu, D, 1);
+          const int A2n = __shfl_down_sync(0xffffffffu, A, 2), B2n = __shfl_down_sync(0xffffffffu, B, 2);
+          o[0] = D + C1n;
+          o[1] = (D - A) + D1n;
+          o[2] = (D - B) + D1n + A2n;
+          o[3] = (D - C) + D1n + B2n;
+        };
+        horiz(sp, o_sp); horiz(sxx, o_xx); horiz(syy, o_yy); horiz(sxy, o_xy);
 #pragma unroll
-          for (int dx = 1; dx < 7; ++dx) {
-            const int4 v = s_cs[buf][t + dx];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-          }
-          const int sx = s.x & 0xffff, sy = (s.x >> 16) & 0xffff;
+        for (int k = 0; k < 4; ++k) {
+          const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
           const int pxy = sx * sy;
-          const int vx = 49 * s.y - sx * sx;        // 48*49 * var_x, exact
-          const int vy = 49 * s.z - sy * sy;
-          const int vxy = 49 * s.w - pxy;           // 48*49 * cov_xy, exact
-          const float a1 = 2.f * (float)pxy + c1s;
-          const float a2 = 2.f * (float)vxy + c2s;
-          const float b1 = (float)(sx * sx + sy * sy) + c1s;
-          const float b2 = (float)(vx + vy) + c2s;
-          acc += (double)__fdiv_rn(a1 * a2, b1 * b2);
+          const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
+          const int vs = 49 * (o_xx[k] + o_yy[k]) - u;        // 48*49 (var_x + var_y), exact
+          const int vxy = 49 * o_xy[k] - pxy;                 // 48*49 cov_xy, exact
+          const float a1 = fmaf(2.f, (float)pxy, c1s);
+          const float a2 = fmaf(2.f, (float)vxy, c2s);
+          const float b1 = (float)u + c1s;
+          const float b2 = (float)vs + c2s;
+          const float den = b1 * b2;
+          float rcp = __frcp_rn(den);                         // 0/0 (constant frames, R = 0) stays NaN
+          rcp = fmaf(rcp, fmaf(-den, rcp, 1.f), rcp);
+          const float sv = (a1 * a2) * rcp;
+          s4 += own[k] ? sv : 0.f;
         }
+        acc += (double)s4;
       }
     }
-    __syncthreads();
+    wa = nwa; wb = nwb; oa = noa; ob = nob;
   }
+  sse += (unsigned long long)sq - 2ull * cr;
 
   acc = warp_sum(acc);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
-  if ((t & 31) == 0) { s_red[t >> 5] = acc; s_red2[t >> 5] = sse; }
-  __syncthreads();
-  if (t == 0) {
-    double a = 0.0; unsigned long long e = 0;
-    for (int i = 0; i < kSsimThreads / 32; ++i) { a += s_red[i]; e += s_red2[i]; }
-    part_ssim[(int64_t)p * nbands + band] = a;
-    part_sse[(int64_t)p * nbands + band] = e;
+  if (lane == 0) {
+    part_ssim[item] = acc;
+    part_sse[item] = sse;
   }
 }
 
@@ -226,18 +259,21 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
 
 struct FrameLayout {
   uint8_t* gray; int2* minmax; double* part_ssim; unsigned long long* part_sse;
-  int bh, nbands; size_t bytes;
+  int pitch, bh, nbands, nchunks, nparts; size_t bytes;
 };
 static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int npairs) {
   Carver c(ws, ws_bytes);
   FrameLayout L{};
-  L.gray = c.take<uint8_t>((size_t)nf * h * w);
+  L.pitch = (w + 3) & ~3;
+  L.gray = c.take<uint8_t>((size_t)nf * h * L.pitch);
   L.minmax = c.take<int2>((size_t)nf);
-  const int out_rows = h >= 7 ? h - 6 : 0;
-  L.bh = 56;
+  const int out_rows = h >= 7 ? h - 6 : 0, out_cols = w >= 7 ? w - 6 : 0;
+  L.bh = kSsimBand;
   L.nbands = out_rows > 0 ? (out_rows + L.bh - 1) / L.bh : 1;
-  L.part_ssim = c.take<double>((size_t)npairs * L.nbands);
-  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nbands);
+  L.nchunks = out_cols > 0 ? (out_cols + kSsimChunk - 1) / kSsimChunk : 1;
+  L.nparts = L.nbands * L.nchunks;
+  L.part_ssim = c.take<double>((size_t)npairs * L.nparts);
+  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts);
   L.bytes = c.used();
   return L;
 }
@@ -277,14 +313,15 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   if (bpf < 1) bpf = 1;
   if (bpf > 64) bpf = 64;
   HIPPO_REQUIRE(nf <= 65535, "hippo_frame_pairs: at most 65535 frames per call");
-  gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, ch, L.gray, L.minmax);
+  gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
   HIPPO_CUDA(cudaGetLastError());
   HIPPO_REQUIRE(npairs <= 65535, "hippo_frame_pairs: at most 65535 pairs per call");
-  ssim_pair_kernel<<<dim3(L.nbands, npairs), kSsimThreads, 0, s>>>(L.gray, h, w, pair_a, pair_b, L.minmax,
-                                                                   range_mode, L.bh, L.nbands, L.part_ssim,
-                                                                   L.part_sse);
+  const int64_t nitems = (int64_t)npairs * L.nparts;
+  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(
+      L.gray, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks, nitems, L.part_ssim,
+      L.part_sse);
   HIPPO_CUDA(cudaGetLastError());
-  ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nbands, h, w,
+  ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nparts, h, w,
                                                            out_ssim, out_mse);
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;

@@ -2,39 +2,47 @@
 // (hm:1002-1114), operation for operation in fp64 (this file is compiled with -fmad=false
 // so that no product feeds a fused add the Python interpreter would have rounded).
 //
-// One CTA of 1024 threads per stream.  The chain over segments is sequential (each boundary
+// One CTA of 256 threads per stream.  The chain over segments is sequential (each boundary
 // anchors the next window), so the kernel is bound by the latency of ONE segment, which is kept
-// at about one global-memory round trip plus three barriers:
+// at about one global-memory round trip plus ONE barrier:
 //   * frame times and adjacent-pair SSIMs are staged in shared memory once (up to kStageFrames
 //     frames);
-//   * the window's frame range [lo, hi] (hm:1045-1048) is found by all threads at once, each testing one
-//     frame from the previous window's start onwards (boundaries only move forward) -- no binary search;
-//   * the backward SSIM scan (hm:1052-1059) tests 1024 pairs per step, the latest hit wins (atomicMax);
-//   * the audio scan (hm:1061-1077) evaluates 64 half-second windows per step, one HALF-WARP per window:
+//   * the window's frame range and the backward SSIM scan (hm:1045-1059) are one pass: every thread tests
+//     one frame from the previous window's start onwards (boundaries only move forward, no binary search),
+//     membership in [lo+1, hi] is decided from the frame's own and its predecessor's time, the latest pair
+//     below the threshold wins (atomicMax);
+//   * the audio scan (hm:1061-1077) evaluates 64 half-second windows per step, four lanes per window:
 //     a 30 s span has at most 59, so one step covers it.  The lanes split the window's pyramid terms
 //     (all loads independent, issued together) and reduce with shuffles; the first window in the
-//     reference's order that is below the threshold wins (atomicMin).  The video work runs in the
-//     shadow of these loads.
-// The scalar state (current_start, current_end, optimal_end) is carried redundantly by all threads.
+//     reference's order that is below the threshold wins (atomicMin).  The threshold test runs in the
+//     power domain (no sqrt / log10 unless the mean is within 1e-12 of the threshold);
+//   * the per-segment picks are triple-buffered in shared memory, so video, audio and the re-arming of
+//     the next segment's slots need no barrier between them.
+// The scalar state (current_start, current_end, optimal_end) is carried redundantly by all threads, which
+// is why the CTA is small: with 32 warps the redundant scalar code alone cost ~8k issue cycles per segment.
 // Window sums are exact for int16-origin PCM (every term is an integer multiple of 2^-30 below 2^53),
 // hence independent of the summation order.
 #include "audio.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace hippo {
 
-constexpr int kSegThreads = 1024;
-constexpr int kSegWindows = kSegThreads / 16;   // audio windows per step
+constexpr int kSegThreads = 256;                // every thread runs the scalar chain redundantly: few warps keep it cheap
+constexpr int kSegLanes = 4;                    // lanes per audio window
+constexpr int kSegWindows = kSegThreads / kSegLanes;   // 64 audio windows per step
+constexpr int kSegBatch = 24;                   // pyramid terms a lane loads before it starts adding
 constexpr int kStageFrames = 6000;     // 2 x 6000 doubles = 96 KB of dynamic shared memory
 
 __device__ __forceinline__ double py_min(double a, double b) { return b < a ? b : a; }  // Python min(a, b)
 
-// Sum of squares of samples [s, e) by one HALF-WARP (hl = lane & 15): head samples up to a 16-boundary,
-// 16-blocks up to a 512-boundary, 512-blocks, 16-blocks, tail samples -- the same terms as
-// window_sumsq_pyramid, dealt round-robin to the 16 lanes.  Every lane returns the sum.
-__device__ __forceinline__ double halfwarp_window_sumsq(const void* pcm, int dtype, int nch,
-                                                        const double* __restrict__ e16,
-                                                        const double* __restrict__ e512, int64_t s, int64_t e,
-                                                        int hl) {
+// Sum of squares of samples [s, e) by kSegLanes adjacent lanes (hl = lane & 3): head samples up to a
+// 16-boundary, 16-blocks up to a 512-boundary, 512-blocks, 16-blocks, tail samples -- the same terms as
+// window_sumsq_pyramid, dealt round-robin to the lanes.  Every lane of the group returns the sum.
+__device__ __forceinline__ double group_window_sumsq(const void* pcm, int dtype, int nch,
+                                                     const double* __restrict__ e16,
+                                                     const double* __restrict__ e512, int64_t s, int64_t e,
+                                                     int hl) {
   double acc = 0.0;
   if (e > s) {
     int64_t a16 = (s + 15) & ~(int64_t)15;      // first 16-boundary >= s
@@ -48,39 +56,55 @@ __device__ __forceinline__ double halfwarp_window_sumsq(const void* pcm, int dty
     const int n_512 = (int)((b512 - a512) >> 9);
     const int n_hi16 = (int)((b16 - b512) >> 4);
     const int n_tail = (int)(e - b16);
-    // edge samples: at most 15 at either end (31 when the window lies inside one 16-block), two per lane
-    double ve = 0.0;
-    for (int t = hl; t < n_head; t += 16) { const double x = pcm_mono(pcm, dtype, nch, s + t); ve += x * x; }
-    for (int t = hl; t < n_tail; t += 16) { const double x = pcm_mono(pcm, dtype, nch, b16 + t); ve += x * x; }
-    // pyramid terms, dealt round-robin; the first eight per lane are issued together (independent loads)
+    // edge samples: at most 15 at either end (31 when the window lies inside one 16-block)
+    for (int t = hl; t < n_head; t += kSegLanes) { const double x = pcm_mono(pcm, dtype, nch, s + t); acc += x * x; }
+    for (int t = hl; t < n_tail; t += kSegLanes) { const double x = pcm_mono(pcm, dtype, nch, b16 + t); acc += x * x; }
+    // pyramid terms, dealt round-robin; 24 per lane are issued together (independent loads): a half-second
+    // window at 16 kHz has at most 77 terms, so its whole sum costs one memory round trip
     const int total = n_lo16 + n_512 + n_hi16;
     const double* lo16p = e16 + (a16 >> 4);
     const double* midp = e512 + (a512 >> 9) - n_lo16;
     const double* hi16p = e16 + (b512 >> 4) - n_lo16 - n_512;
-    double vp[8];
+    for (int t0 = hl; t0 < total; t0 += kSegBatch * kSegLanes) {
+      double vp[kSegBatch];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int t = hl + 16 * u;
-      const double* ptr = t < n_lo16 ? lo16p : (t < n_lo16 + n_512 ? midp : hi16p);
-      vp[u] = t < total ? ptr[t] : 0.0;
-    }
-    acc = ve + ((vp[0] + vp[1]) + (vp[2] + vp[3])) + ((vp[4] + vp[5]) + (vp[6] + vp[7]));
-    for (int t = hl + 128; t < total; t += 16) {
-      const double* ptr = t < n_lo16 ? lo16p : (t < n_lo16 + n_512 ? midp : hi16p);
-      acc += ptr[t];
+      for (int u = 0; u < kSegBatch; ++u) {
+        const int t = t0 + kSegLanes * u;
+        const double* ptr = t < n_lo16 ? lo16p : (t < n_lo16 + n_512 ? midp : hi16p);
+        vp[u] = t < total ? ptr[t] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kSegBatch; u += 4) acc += (vp[u] + vp[u + 1]) + (vp[u + 2] + vp[u + 3]);
     }
   }
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // stays inside the half-warp
+  for (int o = kSegLanes / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // stays inside the group
   return acc;
+}
+
+// `level_db(sumsq, len) < db_thr` (hm:998-999, hm:1073) without the sqrt / log10 / division on the common path:
+// 20 log10(sqrt(m)) < T  <=>  m < 10^(T/10) mathematically, and the reference's fp64 chain is within a few
+// ulp of that, so only a mean within 1e-12 (relative) of the power threshold needs the exact evaluation.
+__device__ __forceinline__ bool below_level(double sumsq, int64_t len, double db_thr, double pow_thr) {
+  if (len <= 0 || !(sumsq > 0.0)) return level_db(sumsq, len) < db_thr;    // -100 (or NaN input): exact path
+  if (pow_thr > 0.0 && pow_thr < 1e300) {
+    const double bound = pow_thr * (double)len;
+    if (sumsq < bound * (1.0 - 1e-12)) return true;
+    if (sumsq > bound * (1.0 + 1e-12)) return false;
+  }
+  return level_db(sumsq, len) < db_thr;
 }
 
 __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_stream_desc* __restrict__ streams,
                                                                  int nstreams, double max_dur, double min_dur,
-                                                                 double ssim_thr, double db_thr) {
+                                                                 double ssim_thr, double db_thr,
+                                                                 unsigned long long* dbg) {
   extern __shared__ double s_stage[];          // [kStageFrames] frame times, [kStageFrames] ssim
-  __shared__ long long s_lo, s_hi, s_vpick;
-  __shared__ int s_apick;
+  // per-segment results, triple-buffered so that ONE barrier per segment suffices: segment k uses set k % 3,
+  // thread 0 re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
+  // left before the barrier of segment k - 1; first written in segment k + 1, after the barrier of segment k)
+  __shared__ long long s_lo[3], s_vpick[3];
+  __shared__ int s_apick[3];
   const int tid = threadIdx.x;
   const int si = blockIdx.x;
   if (si >= nstreams) return;
@@ -101,6 +125,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       ssim = s_stage + kStageFrames;
     }
   }
+  if (tid < 3) { s_lo[tid] = -1; s_vpick[tid] = -1; s_apick[tid] = 0x7fffffff; }
   __syncthreads();
 
   // hm:1027-1032
@@ -109,94 +134,84 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   else if (has_audio) total = (double)S.ns / sr;
   else { if (tid == 0) *S.out_count = 0; return; }
 
+  const double pow_thr = pow(10.0, db_thr / 10.0);
   const int64_t w = has_audio ? (int64_t)(0.5 * sr) : 0;   // hm:1066; the host rejects w < 1 like range() does
+  const bool scan_audio = has_audio && w >= 1;
   int count = 0;
   bool overflow = false;
   int64_t hint = 0;                                  // first frame with t >= current_start so far
   double cs = 0.0;                                   // hm:1034
+  long long t_video = 0, t_audio = 0, t_bar = 0, t_tail = 0, t_a = 0, t_b = 0;
   while (cs < total) {                               // hm:1036
+    const long long c0 = dbg ? clock64() : 0;
+    const int set = count % 3;
+    if (tid == 0) { const int nx = (count + 1) % 3; s_lo[nx] = -1; s_vpick[nx] = -1; s_apick[nx] = 0x7fffffff; }
     const double ce = py_min(cs + max_dur, total);   // hm:1038
     double opt = ce;                                 // hm:1041
     const int64_t s0 = (int64_t)(cs * sr);           // int() truncates toward zero
     const int64_t e0 = (int64_t)(ce * sr);
     const int64_t first = e0 - s0 - w;               // hm:1068: range(first, 0, -w)
 
-    if (tid == 0) { s_lo = -1; s_hi = -2; s_vpick = -1; s_apick = 0x7fffffff; }
-    __syncthreads();
-
-    // ---- video, step 1: indices with cs <= t <= ce form one run [lo, hi] (frame_times is non-decreasing):
-    // lo = first t >= cs (>= hint), hi = last t <= ce (>= hint - 1)
-    int64_t lo = nf, hi = nf - 1;
+    // ---- video (hm:1045-1059).  The indices with cs <= t <= ce form one run [lo, hi] (frame_times is
+    // non-decreasing) and lo >= hint (boundaries only move forward).  The scan i = hi .. lo+1 stops at the first
+    // pair (frame i, frame i-1) with ssim[i-1] < threshold, i.e. the LARGEST such i: every thread tests one frame
+    // per step -- i is in the scan iff t[i-1] >= cs (i-1 >= lo) and t[i] <= ce (i <= hi) -- and atomicMax keeps it.
     if (has_video) {
-      if (tid == 0 && (hint >= nf || ftimes[hint] > ce)) s_hi = hint - 1;
-      for (int64_t base = hint;; base += kSegThreads) {
+      for (int64_t base = hint; base < nf; base += kSegThreads) {
         const int64_t i = base + tid;
         if (i < nf) {
           const double t = ftimes[i];
-          if (t >= cs && (i == hint || ftimes[i - 1] < cs)) s_lo = i;
-          if (t <= ce && (i == nf - 1 || ftimes[i + 1] > ce)) s_hi = i;
+          const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
+          if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
+          if (ssim != nullptr && i > hint && tp >= cs && t <= ce && ssim[i - 1] < ssim_thr)   // NaN compares false, as in Python
+            atomicMax(&s_vpick[set], (long long)i);
         }
-        if (base + kSegThreads >= nf) break;
-        __syncthreads();
-        if (s_lo >= 0 && s_hi >= -1) break;          // uniform: read after the barrier, written before it
-        __syncthreads();
+        const int64_t last = base + kSegThreads - 1;
+        if (last >= nf - 1 || ftimes[last] > ce) break;                      // uniform: the run ends inside this step
       }
     }
+    const long long c1 = dbg ? clock64() : 0;
 
-    // ---- audio (hm:1061-1077; runs second in the reference and overwrites the video boundary): first step
-    // of 64 windows issued now, its loads overlap the rest of the video work
-    bool more_audio = false;
-    if (has_audio && w >= 1) {
-      const int64_t i = first - (int64_t)(tid >> 4) * w;   // one half-warp per window
-      double ss = 0.0;
+    // ---- audio (hm:1061-1077; runs second in the reference and overwrites the video boundary)
+    if (scan_audio) {
+      const int64_t i = first - (int64_t)(tid / kSegLanes) * w;   // four lanes per window
       int64_t ws = 0, we = 0;
       if (i > 0) {
         ws = s0 + i; we = ws + w;                    // audio_data[window_start:window_end] clips
         if (ws > S.ns) ws = S.ns;
         if (we > S.ns) we = S.ns;
       }
-      ss = halfwarp_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & 15);
-      if (i > 0 && (tid & 15) == 0 && level_db(ss, we - ws) < db_thr) atomicMin(&s_apick, tid >> 4);
-      more_audio = first - (int64_t)kSegWindows * w > 0;
+      const double ss = group_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & (kSegLanes - 1));
+      if (i > 0 && (tid & (kSegLanes - 1)) == 0 && below_level(ss, we - ws, db_thr, pow_thr)) atomicMin(&s_apick[set], tid / kSegLanes);
     }
+    const long long c2 = dbg ? clock64() : 0;
     __syncthreads();
+    const long long c3 = dbg ? clock64() : 0;
 
-    // ---- video, step 2 (hm:1050-1059): scan i = hi .. lo+1, pair (frame i, frame i-1) = ssim[i-1]
     if (has_video) {
-      lo = s_lo >= 0 ? s_lo : nf;
-      hi = s_hi >= -1 ? s_hi : nf - 1;
-      hint = lo;
+      const long long lo = s_lo[set], pick = s_vpick[set];
+      hint = lo >= 0 ? lo : nf;
+      if (pick >= 0) opt = ftimes[pick];             // hm:1057
     }
-    int apick = s_apick;
-    if (has_video && hi - lo + 1 > 1 && ssim != nullptr) {
-      for (int64_t top = hi; top > lo; top -= kSegThreads) {
-        const int64_t i = top - tid;
-        if (i > lo && ssim[i - 1] < ssim_thr) atomicMax(&s_vpick, (long long)i);   // NaN compares false, as in Python
-        __syncthreads();
-        const long long pick = s_vpick;
-        if (pick >= 0) { opt = ftimes[pick]; break; }
-        if (top - kSegThreads > lo) __syncthreads();
-      }
-    }
-
-    if (has_audio && w >= 1) {
-      // further steps only when the span holds more than 64 windows (max_segment_duration > 32 s)
+    const long long c3a = dbg ? clock64() : 0;
+    if (scan_audio) {
+      int apick = s_apick[set];
       int64_t base = first;
-      while (apick == 0x7fffffff && more_audio) {
+      // further steps only when the span holds more than 64 windows (max_segment_duration > 32 s)
+      while (apick == 0x7fffffff && base - (int64_t)kSegWindows * w > 0) {
         base -= (int64_t)kSegWindows * w;
         __syncthreads();                              // everyone has read s_apick
-        const int64_t i = base - (int64_t)(tid >> 4) * w;
+        const int64_t i = base - (int64_t)(tid / kSegLanes) * w;
         int64_t ws = 0, we = 0;
         if (i > 0) {
           ws = s0 + i; we = ws + w;
           if (ws > S.ns) ws = S.ns;
           if (we > S.ns) we = S.ns;
         }
-        const double ss = halfwarp_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & 15);
-        if (i > 0 && (tid & 15) == 0 && level_db(ss, we - ws) < db_thr) atomicMin(&s_apick, tid >> 4);
+        const double ss = group_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & (kSegLanes - 1));
+        if (i > 0 && (tid & (kSegLanes - 1)) == 0 && below_level(ss, we - ws, db_thr, pow_thr)) atomicMin(&s_apick[set], tid / kSegLanes);
         __syncthreads();
-        apick = s_apick;
-        more_audio = base - (int64_t)kSegWindows * w > 0;
+        apick = s_apick[set];
       }
       if (apick != 0x7fffffff) {
         const int64_t iw = base - (int64_t)apick * w;
@@ -204,6 +219,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       }
     }
 
+    const long long c3b = dbg ? clock64() : 0;
     // hm:1080-1084
     if (opt - cs < min_dur) opt = py_min(cs + min_dur, total);
 
@@ -215,9 +231,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     }
     ++count;
     cs = opt;                                        // hm:1111
-    __syncthreads();                                 // the shared picks are re-armed at the top
+    if (dbg) { const long long c4 = clock64(); t_video += c1 - c0; t_audio += c2 - c1; t_bar += c3 - c2; t_tail += c4 - c3; t_a += c3a - c3; t_b += c3b - c3a; }
   }
   if (tid == 0) *S.out_count = overflow ? -1 : count;
+  if (dbg && tid == 0 && si == 0) { dbg[0] = t_video; dbg[1] = t_audio; dbg[2] = t_bar; dbg[3] = t_tail; dbg[4] = t_a; dbg[5] = t_b; dbg[6] = count; }
 }
 
 }  // namespace hippo
@@ -234,9 +251,19 @@ extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* stream
   if (st != HIPPO_OK) return st;
   const size_t smem = (size_t)2 * kStageFrames * sizeof(double);
   HIPPO_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned long long* dbg = nullptr;
+  if (getenv("HIPPO_SEG_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
   segment_kernel<<<nstreams, kSegThreads, smem, (cudaStream_t)stream>>>(
       streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
-      audio_silence_threshold);
+      audio_silence_threshold, dbg);
+  if (dbg) {
+    unsigned long long h[8];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    fprintf(stderr, "[seg] %llu segments; cycles/segment: video %.0f audio %.0f barrier %.0f tail %.0f (reads %.0f, audio pick %.0f)\n", h[6],
+            (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+  }
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
