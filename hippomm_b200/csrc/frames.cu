@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
   unsigned long long sse = 0;
   uint32_t sq = 0, cr = 0;                        // sum a^2 + b^2, sum a b of the rows owned for the squared error
 
-  auto ldw = [&](const uint8_t* g, int r) -> uint32_t {
-    return (col_ok && r >= y0 && r < h) ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
+  auto ldw = [&](const uint8_t* g, int r) -> uint32_t {   // callers pass r >= y0; rows past the frame read as zero
+    return (col_ok && r < h) ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
   };
   uint32_t wa = ldw(ga, y0), wb = ldw(gb, y0), oa = 0, ob = 0;
   for (int r = y0; r < rend; ++r) {
@@ -201,13 +201,14 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
         float s4 = 0.f;
         int o_sp[4], o_xx[4], o_yy[4], o_xy[4];
         auto horiz = [&](const int (&c)[4], int (&o)[4]) {
-          const int A = c[0], B = A + c[1], C = B + c[2], D = C + c[3];
-          const int C1n = __shfl_down_sync(0xffffffffu, C, 1), D1n = __shfl_down_sync(0xffffffffu, D, 1);
-          const int A2n = __shfl_down_sync(0xffffffffu, A, 2), B2n = __shfl_down_sync(0xffffffffu, B, 2);
+          // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
+          const int C = c[0] + c[1] + c[2], D = C + c[3];
+          const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c[3], 1);
+          const int m0 = __shfl_down_sync(0xffffffffu, c[0], 2), m1 = __shfl_down_sync(0xffffffffu, c[1], 2);
           o[0] = D + C1n;
-          o[1] = (D - A) + D1n;
-          o[2] = (D - B) + D1n + A2n;
-          o[3] = (D - C) + D1n + B2n;
+          o[1] = o[0] + n3 - c[0];
+          o[2] = o[1] + m0 - c[1];
+          o[3] = o[2] + m1 - c[2];
         };
         horiz(sp, o_sp); horiz(sxx, o_xx); horiz(syy, o_yy); horiz(sxy, o_xy);
 #pragma unroll
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
           const float b1 = (float)u + c1s;
           const float b2 = (float)vs + c2s;
           const float den = b1 * b2;
-          float rcp = __frcp_rn(den);                         // 0/0 (constant frames, R = 0) stays NaN
-          rcp = fmaf(rcp, fmaf(-den, rcp, 1.f), rcp);
+          float rcp;                                          // 1 ulp; 0 * inf (constant frames, R = 0) stays NaN like 0/0
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
           const float sv = (a1 * a2) * rcp;
           s4 += own[k] ? sv : 0.f;
         }
