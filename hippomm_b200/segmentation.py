@@ -181,17 +181,7 @@ def compute_audio_level(audio_data, sample_rate=None) -> float:
 
 
 # ------------------------------------------------------------ segmentation ----
-def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],
-                              pcm: Optional[torch.Tensor], pyramid, sample_rate, max_segment_duration: float,
-                              min_segment_duration: float, frame_similarity_threshold: float,
-                              audio_silence_threshold: float, max_segments: int):
-    """One stream through hippo_segment_boundaries. Returns (bounds fp64 [max_segments, 2], count int32 [1])."""
-    lib = _lib.load()
-    ref = frame_times if frame_times is not None else pcm
-    dev = _cuda.require_device(ref.device)
-    bounds = torch.empty((max_segments, 2), dtype=torch.float64, device=dev)
-    count = torch.zeros((1,), dtype=torch.int32, device=dev)
-    desc = _lib.StreamDesc()
+def _fill_stream_desc(desc, ssim, frame_times, pcm, pyramid, sample_rate, bounds, count, max_segments):
     desc.ssim = _cuda.ptr(ssim) if ssim is not None and ssim.numel() > 0 else None
     desc.frame_times = _cuda.ptr(frame_times)
     desc.nframes = 0 if frame_times is None else frame_times.numel()
@@ -205,13 +195,44 @@ def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optiona
     desc.out_bounds = bounds.data_ptr()
     desc.out_count = count.data_ptr()
     desc.max_segments = max_segments
-    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(desc), ctypes.sizeof(desc)), dtype=np.uint8).copy()
+
+
+def segment_boundaries_batch_device(streams, max_segment_duration: float, min_segment_duration: float,
+                                    frame_similarity_threshold: float, audio_silence_threshold: float,
+                                    max_segments: int):
+    """Several independent streams through ONE hippo_segment_boundaries launch (one CTA per stream: the
+    sequential boundary chains of different streams run side by side).  `streams` is a list of
+    (ssim, frame_times, pcm, pyramid, sample_rate) tuples of device tensors, entries None as for the
+    single-stream call.  Returns (bounds fp64 [n, max_segments, 2], counts int32 [n])."""
+    lib = _lib.load()
+    n = len(streams)
+    if n == 0:
+        raise ValueError("no streams")
+    ref = next(t for st in streams for t in (st[1], st[2]) if t is not None)
+    dev = _cuda.require_device(ref.device)
+    bounds = torch.empty((n, max_segments, 2), dtype=torch.float64, device=dev)
+    counts = torch.zeros((n,), dtype=torch.int32, device=dev)
+    descs = (_lib.StreamDesc * n)()
+    for i, (ssim, ft, pcm, pyr, sr) in enumerate(streams):
+        _fill_stream_desc(descs[i], ssim, ft, pcm, pyr, sr, bounds[i], counts[i:i + 1], max_segments)
+    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(descs), ctypes.sizeof(descs)), dtype=np.uint8).copy()
     desc_dev = torch.from_numpy(raw).to(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.hippo_segment_boundaries(
-            desc_dev.data_ptr(), 1, float(max_segment_duration), float(min_segment_duration),
+            desc_dev.data_ptr(), n, float(max_segment_duration), float(min_segment_duration),
             float(frame_similarity_threshold), float(audio_silence_threshold), _cuda.stream_ptr()))
-    return bounds, count
+    return bounds, counts
+
+
+def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],
+                              pcm: Optional[torch.Tensor], pyramid, sample_rate, max_segment_duration: float,
+                              min_segment_duration: float, frame_similarity_threshold: float,
+                              audio_silence_threshold: float, max_segments: int):
+    """One stream through hippo_segment_boundaries. Returns (bounds fp64 [max_segments, 2], count int32 [1])."""
+    bounds, counts = segment_boundaries_batch_device(
+        [(ssim, frame_times, pcm, pyramid, sample_rate)], max_segment_duration, min_segment_duration,
+        frame_similarity_threshold, audio_silence_threshold, max_segments)
+    return bounds[0], counts
 
 
 def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio_sample_rate=None, *,

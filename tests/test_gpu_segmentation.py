@@ -161,3 +161,31 @@ def test_one_hour_stream_against_oracle(cuda_device):
     want = O.segment_boundaries(ss, times, x.reshape(-1, 1), 16000)
     assert [(s.start_time, s.end_time) for s in segs] == want
     assert 100 <= len(segs) <= 400
+
+
+def test_batched_streams_match_single_stream_calls(cuda_device):
+    """Three different streams (video+audio, audio only, video only) through one launch == one launch each."""
+    from hippomm_b200 import synth
+    from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device,
+                                           segment_boundaries_batch_device, segment_boundaries_device)
+
+    sr = 16000
+    streams = []
+    for seed, (nsec, video, audio) in enumerate([(150, True, True), (95, False, True), (120, True, False)]):
+        ssim = ft = pcm = pyr = None
+        if video:
+            frames, _ = synth.frame_stream(10 + seed, nsec, 48, 64, min_scene=5, max_scene=25)
+            fd = torch.from_numpy(frames).to(cuda_device)
+            ssim, _ = frame_pair_scores_device(fd, range_mode=0)
+            ft = torch.arange(nsec, dtype=torch.float64, device=cuda_device)
+        if audio:
+            pcm = torch.from_numpy(synth.audio_stream_int16(20 + seed, nsec * sr).reshape(-1, 1)).to(cuda_device)
+            pyr = audio_energy_device(pcm)
+        streams.append((ssim, ft, pcm, pyr, sr if audio else None))
+    bounds, counts = segment_boundaries_batch_device(streams, 30.0, 10.0, 0.95, -40.0, 64)
+    torch.cuda.synchronize()
+    for i, st in enumerate(streams):
+        b1, c1 = segment_boundaries_device(*st, 30.0, 10.0, 0.95, -40.0, 64)
+        c = int(c1.item())
+        assert c > 0 and int(counts[i].item()) == c
+        assert torch.equal(bounds[i, :c], b1[:c])
