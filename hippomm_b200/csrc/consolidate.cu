@@ -1,27 +1,46 @@
 // hippo_consolidate: greedy cosine-redundancy filter (reference: _select_key_frames, hm:944-967).
 //
-//   1. hippo_bank_build      fp32 rows -> bf16 rows + fp32 norms              (hm:951)
-//   2. sim_tc EPI_MASK       lower-triangle similarity bits on tcgen05        (hm:952, hm:960)
-//   3. recheck_kernel        pairs within `band` of gamma re-evaluated from the fp32 rows
-//   4. greedy_scan_kernel    row i kept iff no kept j < i has bit (i, j)      (hm:958-961)
-//   5. compact_kernel        kept bitmap -> ascending int64 row numbers       (hm:967)
+// The reference forms the whole N x N similarity matrix (hm:952) and then walks the rows: row i is kept iff
+// every KEPT earlier row j has sim(i, j) < gamma (hm:958-961).  Similarities against rows that were dropped
+// are never looked at -- and on video-like input most rows are dropped.  So the rows are processed in BANDS
+// of kConsBand rows, and a band is only contracted against
+//     (a) the rows kept so far, held compacted at the front of a second bf16 matrix Y, and
+//     (b) itself (lower triangle),
+// which is exactly the set of pairs the greedy rule can consult.  With K rows kept out of N the tensor work
+// drops from N^2/2 to about N K / 2 + N band / 2 pairs (10x at 6% kept); when everything is kept it is the
+// full triangle again.  The decisions are identical either way.
 //
-// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed; the bit
-// matrix is N^2/8 bytes.
+//   0. hippo_bank_build       fp32 rows -> bf16 rows X + fp32 norms                (hm:951)
+//   per band (all asynchronous, the extent of a band's work is read from device memory):
+//   1. cons_advance_kernel    finishes the previous band (its kept rows are compacted to Y[K ..), K grows,
+//                             the caller's out_keep receives their row numbers) and copies this band's rows
+//                             to Y[K .. K + rows)
+//   2. sim_tc EPI_MASK        similarity bits of Y rows [K, K + rows) against Y rows before them, on tcgen05
+//                                                                                 (hm:952, hm:960)
+//   3. recheck_kernel         pairs within `band` of gamma re-evaluated from the fp32 rows
+//   4. greedy_scan_kernel     row i kept iff no kept j < i has bit (i, j)           (hm:958-961)
+//
+// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed; the bit matrix is N^2/8 bytes
+// in the worst case (everything kept), and only the rows of the current band are ever live.
 #include "common.cuh"
 #include "sim_tc.cuh"
-#include <vector>
+
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace hippo {
 
+constexpr int kConsBandDefault = 4096;
+
 // ---- 3. exact re-evaluation of near-threshold pairs ---------------------------------
-// One warp per pair.  Rows are normalised element-wise in fp32 exactly like hm:951
-// (x / |x| with the fp32 norm), the products are accumulated in fp64, and the bit becomes
-// !(sim < gamma) -- the best available stand-in for the reference's fp32 sgemm value.
+// One warp per pair (i, j) of Y rows.  The rows are looked up in the caller's fp32 matrix through yidx,
+// normalised element-wise in fp32 exactly like hm:951 (x / |x| with the fp32 norm), the products are
+// accumulated in fp64, and the bit becomes !(sim < gamma) -- the best available stand-in for the
+// reference's fp32 sgemm value.
 __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ feats,
                                                       const float* __restrict__ norm, int d,
+                                                      const int64_t* __restrict__ yidx,
                                                       float gamma, const uint2* __restrict__ pairs,
                                                       const int32_t* __restrict__ count, int32_t cap,
                                                       uint32_t* __restrict__ mask, int64_t words_per_row) {
@@ -32,9 +51,10 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
   if (np > cap) np = cap;
   for (int64_t pi = warp; pi < np; pi += nwarps) {
     const uint2 pr = pairs[pi];
-    const float* a = feats + (int64_t)pr.x * d;
-    const float* b = feats + (int64_t)pr.y * d;
-    const float na = norm[pr.x], nb = norm[pr.y];
+    const int64_t ra = yidx[pr.x], rb = yidx[pr.y];
+    const float* a = feats + ra * d;
+    const float* b = feats + rb * d;
+    const float na = norm[ra], nb = norm[rb];
     double acc = 0.0;
     for (int c = lane * 4; c < d; c += 128) {
       const float4 x = *reinterpret_cast<const float4*>(a + c);
@@ -54,14 +74,17 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
   }
 }
 
-// ---- 4. greedy scan over the bit matrix ------------------------------------------------
-// CTA b owns rows [512 b, 512 b + 512), one thread per row.  The chain over blocks is sequential (a row's
-// fate depends on which earlier rows were KEPT), so the kernel is bound by the hand-off latency between
-// consecutive blocks; everything that does not depend on the predecessors' results is done ahead of them:
+// ---- 4. greedy scan over the bit matrix of one band --------------------------------------
+// Rows are numbered in Y space: rows [0, K) are final (kept), the band is [K, n), n = K + band_rows.  CTA x
+// owns the 512 rows of block b = K / 512 + x, one thread per row (rows of the first block that lie below K
+// are simply resolved again: kept rows never conflict with each other).  The chain over blocks is sequential
+// (a row's fate depends on which earlier rows were KEPT), so the kernel is bound by the hand-off latency
+// between consecutive blocks; everything that does not depend on the predecessors' results is done ahead:
 //   * kept-words are published as self-validating 64-bit values (tag << 32 | word), so a consumer polls
 //     the data itself -- one L2 round trip per hand-off, no separate flag, no fence.  One warp per CTA
 //     polls, and CTAs far behind the frontier sleep between polls: a line hammered by every waiting warp
-//     of the grid delayed the publisher's store by ~5 us (profiles/);
+//     of the grid delayed the publisher's store by ~5 us (profiles/).  Blocks below K need no polling:
+//     all their rows are kept;
 //   * a thread holds its row's mask words against the block itself and its three predecessors in
 //     registers; blocks further back are folded in from global memory as they are published (they are
 //     final well before this block is on the critical path);
@@ -105,19 +128,24 @@ __device__ __forceinline__ uint32_t and_any16(const uint32_t (&words)[kScanWords
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint32_t* __restrict__ mask,
-                                                                      int64_t words_per_row, int64_t n,
-                                                                      unsigned long long* kept /*[blocks * 16], zeroed*/,
+                                                                      int64_t words_per_row,
+                                                                      const int32_t* __restrict__ dyn_k, int band_rows,
+                                                                      unsigned long long* kept /*[grid * 16], zeroed*/,
                                                                       unsigned long long* dbg) {
   __shared__ __align__(16) uint32_t s_kept[2][kScanWords];
   __shared__ __align__(16) uint32_t s_undec[2][kScanWords];
   __shared__ __align__(16) uint32_t s_kw[2][kScanWords];            // bulk ring
   __shared__ __align__(16) uint32_t s_pk[kScanPreds][kScanWords];   // predecessors' kept-words
-  const int b = blockIdx.x;
+  const int kfinal = *dyn_k;
+  const int64_t n = (int64_t)kfinal + band_rows;
+  const int b0 = kfinal / kScanRows;               // first block of this launch; blocks below it are all kept
+  const int b = b0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t row = (int64_t)b * kScanRows + tid;
+  if ((int64_t)b * kScanRows >= n) return;         // nobody waits for a block past the end
   const bool live = row < n;
   auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-  if (dbg && tid == 0) dbg[b * 8 + 0] = now();
+  if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = now();
 
   // this row against its own block (bits j < row only; later words were never written) and the three before
   uint32_t dg[kScanWords], pp[kScanPreds][kScanWords];
@@ -138,12 +166,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
     for (int j = 0; j < kScanPreds; ++j)
       if (b - 1 - j >= 0) load_row_words(mask, words_per_row, row, b - 1 - j, pp[j]);
   }
-  uint32_t ext = 0;
+  // a predecessor below b0 is already known (all kept): only predecessors of this launch can block a row
+  bool blocked = false;
 #pragma unroll
-  for (int w = 0; w < kScanWords; ++w)
+  for (int j = 0; j < kScanPreds; ++j) {
+    uint32_t e = 0;
 #pragma unroll
-    for (int j = 0; j < kScanPreds; ++j) ext |= pp[j][w];
-  bool blocked = ext != 0;          // depends on a predecessor that has not published yet
+    for (int w = 0; w < kScanWords; ++w) e |= pp[j][w];
+    if (b - 1 - j >= b0 && e != 0) blocked = true;
+  }
 
   // blocks 0 .. b-4 from global memory, one block (16 kept-words) per step; warp 0 polls
   uint32_t hit = 0;
@@ -157,9 +188,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
 #pragma unroll
       for (int i = 0; i < 4; ++i) m[i] = __ldg(p + i);
     }
+    if (g < b0) {                                  // rows of a finished band: all kept, nothing to wait for
+      hit |= (m[0].x | m[0].y | m[0].z | m[0].w) | (m[1].x | m[1].y | m[1].z | m[1].w) |
+             (m[2].x | m[2].y | m[2].z | m[2].w) | (m[3].x | m[3].y | m[3].z | m[3].w);
+      continue;
+    }
     if (wid == 0 && lane < kScanWords) {
       unsigned long long v;
-      while (!((v = kept_poll(&kept[(int64_t)g * kScanWords + lane])) >> 32))
+      while (!((v = kept_poll(&kept[(int64_t)(g - b0) * kScanWords + lane])) >> 32))
         if (b - g > 6) __nanosleep(2000);
       s_kw[g & 1][lane] = (uint32_t)v;
     }
@@ -171,7 +207,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
       hit |= (m[i].x & q.x) | (m[i].y & q.y) | (m[i].z & q.z) | (m[i].w & q.w);
     }
   }
-  if (dbg && tid == 0) dbg[b * 8 + 1] = now();
+  // predecessors that belong to finished bands need no hand-off either
+#pragma unroll
+  for (int j = 0; j < kScanPreds; ++j) {
+    if (b - 1 - j >= 0 && b - 1 - j < b0) {
+#pragma unroll
+      for (int w = 0; w < kScanWords; ++w) hit |= pp[j][w];
+    }
+  }
+  if (dbg && tid == 0) dbg[blockIdx.x * 8 + 1] = now();
 
   bool undec = live && hit == 0;
   bool kept_me = false;
@@ -195,22 +239,24 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
     ++round;   // the buffer written last stays intact for the next call's first barrier
   };
   run_rounds();                                       // phase A
-  if (dbg && tid == 0) { dbg[b * 8 + 5] = now(); dbg[b * 8 + 6] = round; }
+  if (dbg && tid == 0) { dbg[blockIdx.x * 8 + 5] = now(); dbg[blockIdx.x * 8 + 6] = round; }
 
-  // phase B: the three predecessors' kept-words (b-3 and b-2 by warp 0, b-1 by warp 1)
-  if (b >= 1) {
+  // phase B: the kept-words of the predecessors that belong to this launch (b-3 and b-2 by warp 0, b-1 by warp 1)
+  if (b - 1 >= b0) {
     if (wid < 2) {
       const int j = wid == 0 ? 2 - (lane >> 4) : 0;   // predecessor b-1-j
-      if ((wid == 0 || lane < kScanWords) && b - 1 - j >= 0) {
-        unsigned long long v;
-        while (!((v = kept_poll(&kept[(int64_t)(b - 1 - j) * kScanWords + (lane & 15)])) >> 32)) {}
-        s_pk[j][lane & 15] = (uint32_t)v;
-      } else if (wid == 0 || lane < kScanWords) {
-        s_pk[j][lane & 15] = 0;
+      if (wid == 0 || lane < kScanWords) {
+        uint32_t kwv = 0;
+        if (b - 1 - j >= b0) {
+          unsigned long long v;
+          while (!((v = kept_poll(&kept[(int64_t)(b - 1 - j - b0) * kScanWords + (lane & 15)])) >> 32)) {}
+          kwv = (uint32_t)v;
+        }
+        s_pk[j][lane & 15] = kwv;                     // finished-band predecessors were folded in above
       }
     }
     __syncthreads();
-    if (dbg && tid == 0) dbg[b * 8 + 2] = now();
+    if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = now();
     if (blocked) {
       uint32_t h = 0;
 #pragma unroll
@@ -219,45 +265,94 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
       blocked = false;
     }
     run_rounds();
-  } else if (dbg && tid == 0) dbg[b * 8 + 2] = now();
+  } else if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = now();
 
   {
     const uint32_t kwd = __ballot_sync(0xffffffffu, kept_me);
-    if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&kept[(int64_t)b * kScanWords + wid]) = kKeptTag | kwd;
-    if (dbg && tid == 0) { dbg[b * 8 + 3] = now(); dbg[b * 8 + 4] = round; }
+    if (lane == 0)
+      *reinterpret_cast<volatile unsigned long long*>(&kept[(int64_t)blockIdx.x * kScanWords + wid]) = kKeptTag | kwd;
+    if (dbg && tid == 0) { dbg[blockIdx.x * 8 + 3] = now(); dbg[blockIdx.x * 8 + 4] = round; }
   }
 }
 
-// ---- 5. kept bitmap -> ascending row numbers ---------------------------------------------
-__global__ void __launch_bounds__(1024) compact_kernel(const unsigned long long* __restrict__ kept, int64_t nwords,
-                                                       int64_t n, int64_t* __restrict__ out_keep,
-                                                       int32_t* __restrict__ out_count) {
-  __shared__ int64_t s_sum[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (nwords + 1023) / 1024;
-  const int64_t w0 = t * per, w1 = min(w0 + per, nwords);
-  int64_t c = 0;
-  for (int64_t w = w0; w < w1; ++w) c += __popc((uint32_t)kept[w]);
-  s_sum[t] = c;
+// ---- 1. finish the previous band, stage the next one -----------------------------------------
+// dyn[par_in] = K before the previous band, whose rows sit at Y[K, K + prev_rows) (original rows prev_r0 ..)
+// and whose kept-words are kept_prev (block-local: bit position = Y row - 512 * (K / 512)).  The kept rows
+// are compacted to Y[K, K'), out_keep[K ..) receives their original row numbers (ascending: hm:967), K' goes
+// to dyn[par_in ^ 1], and the next band's rows [next_r0, next_r0 + next_rows) are copied to Y[K', ...).
+// Everything is read from X (the bf16 image of the caller's rows), never from Y, so the compaction cannot
+// trample rows it still needs.  Every CTA recomputes the (short) prefix over the kept-words on its own.
+constexpr int kAdvThreads = 256;
+constexpr int kAdvMaxWords = 1024;   // band of at most 32k - 512 rows
+
+__global__ void __launch_bounds__(kAdvThreads) cons_advance_kernel(
+    const __nv_bfloat16* __restrict__ X, const float* __restrict__ xnorm, int d, __nv_bfloat16* __restrict__ Y,
+    float* __restrict__ ynorm, int64_t* __restrict__ yidx, const unsigned long long* __restrict__ kept_prev,
+    unsigned long long* __restrict__ kept_next, int kept_words, int32_t* dyn, int par_in, int64_t prev_r0,
+    int prev_rows, int64_t next_r0, int next_rows, int32_t* unc_count, int32_t unc_cap, int32_t* stats) {
+  __shared__ int s_pref[kAdvMaxWords + 1];
+  __shared__ uint32_t s_bits[kAdvMaxWords];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = dyn[par_in];
+  const int off = K - (K / kScanRows) * kScanRows;        // block-local position of Y row K
+  const int nwords = prev_rows > 0 ? (off + prev_rows + 31) / 32 : 0;
+  for (int w = tid; w < nwords; w += kAdvThreads) {
+    uint32_t bits = (uint32_t)kept_prev[w];
+    if (w == off / 32) bits &= ~((1u << (off & 31)) - 1u);            // rows below K are old
+    if (w < off / 32) bits = 0;
+    const int end = off + prev_rows - w * 32;                          // rows past the band
+    if (end < 32) bits &= (1u << end) - 1u;
+    s_bits[w] = bits;
+  }
   __syncthreads();
-  // inclusive scan (Hillis-Steele; 1024 entries, one launch per consolidation)
-  for (int o = 1; o < 1024; o <<= 1) {
-    int64_t v = t >= o ? s_sum[t - o] : 0;
-    __syncthreads();
-    s_sum[t] += v;
-    __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int w = 0; w < nwords; ++w) { s_pref[w] = acc; acc += __popc(s_bits[w]); }
+    s_pref[nwords] = acc;
   }
-  int64_t pos = s_sum[t] - c;
-  for (int64_t w = w0; w < w1; ++w) {
-    uint32_t bits = (uint32_t)kept[w];   // low half of the tagged word
-    while (bits) {
-      const int bpos = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int64_t row = w * 32 + bpos;
-      if (row < n) out_keep[pos++] = row;
-    }
+  __syncthreads();
+  const int added = s_pref[nwords];
+  const int K2 = K + added;
+
+  const int64_t warp = (int64_t)blockIdx.x * (kAdvThreads / 32) + (tid >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kAdvThreads / 32);
+  const int vec_per_row = d / 8;                                       // 16-byte vectors per bf16 row
+  // compaction: one warp per kept row
+  for (int64_t t = warp; t < prev_rows; t += nwarps) {
+    const int pos = off + (int)t;
+    const uint32_t bits = s_bits[pos >> 5];
+    if (!((bits >> (pos & 31)) & 1u)) continue;
+    const int rank = s_pref[pos >> 5] + __popc(bits & ((1u << (pos & 31)) - 1u));
+    const int64_t src = prev_r0 + t, dst = (int64_t)K + rank;
+    const uint4* sp = reinterpret_cast<const uint4*>(X + src * d);
+    uint4* dp = reinterpret_cast<uint4*>(Y + dst * d);
+    for (int v = lane; v < vec_per_row; v += 32) dp[v] = sp[v];
+    if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
   }
-  if (t == 1023) *out_count = (int32_t)s_sum[1023];
+  // next band
+  for (int64_t t = warp; t < next_rows; t += nwarps) {
+    const int64_t src = next_r0 + t, dst = (int64_t)K2 + t;
+    const uint4* sp = reinterpret_cast<const uint4*>(X + src * d);
+    uint4* dp = reinterpret_cast<uint4*>(Y + dst * d);
+    for (int v = lane; v < vec_per_row; v += 32) dp[v] = sp[v];
+    if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
+  }
+  // the next band's hand-off words, the uncertain-pair list, the running statistics
+  for (int64_t i = (int64_t)blockIdx.x * kAdvThreads + tid; i < kept_words; i += (int64_t)gridDim.x * kAdvThreads)
+    kept_next[i] = 0;
+  if (blockIdx.x == 0 && tid == 0) {
+    dyn[par_in ^ 1] = K2;
+    const int32_t c = *unc_count;
+    stats[0] += c < unc_cap ? c : unc_cap;
+    if (c > unc_cap) stats[1] = 1;
+    *unc_count = 0;
+  }
+}
+
+__global__ void cons_finish_kernel(const int32_t* dyn, int par, const int32_t* inexact, const int32_t* stats,
+                                   int32_t* out_count, int32_t* out_stats) {
+  *out_count = dyn[par];
+  if (out_stats) { out_stats[0] = stats[0]; out_stats[1] = stats[1]; out_stats[2] = *inexact; out_stats[3] = 0; }
 }
 
 __global__ void iota_kernel(int64_t n, int64_t* out_keep, int32_t* out_count) {
@@ -265,36 +360,41 @@ __global__ void iota_kernel(int64_t n, int64_t* out_keep, int32_t* out_count) {
   if (threadIdx.x == 0) *out_count = (int32_t)n;
 }
 
-__global__ void stats_kernel(const int32_t* unc_count, int32_t cap, const int32_t* inexact, int32_t* out_stats) {
-  const int32_t c = *unc_count;
-  out_stats[0] = c < cap ? c : cap;
-  out_stats[1] = c > cap ? 1 : 0;
-  out_stats[2] = *inexact;
-  out_stats[3] = 0;
+static int cons_band() {
+  const char* e = getenv("HIPPO_CONS_BAND");
+  int b = e ? atoi(e) : kConsBandDefault;
+  if (b < kScanRows) b = kScanRows;
+  if (b > (kAdvMaxWords - 32) * 32) b = (kAdvMaxWords - 32) * 32;
+  return b / kScanRows * kScanRows;
 }
 
 struct ConsLayout {
-  __nv_bfloat16* bf;
-  float* norm;
-  uint32_t* mask;
+  __nv_bfloat16* X;        // bf16 image of the caller's rows
+  float* xnorm;
+  __nv_bfloat16* Y;        // kept rows so far, compacted, followed by the current band
+  float* ynorm;
+  uint32_t* mask;          // bit matrix in Y row numbers
   int64_t words_per_row;
-  unsigned long long* kept;   // tagged kept-words (greedy_scan_kernel)
-  int64_t kept_words;
+  unsigned long long* kept[2];   // block-local tagged kept-words of the current / next band
+  int kept_words;
   uint2* unc;
   int32_t unc_cap;
-  int32_t* counters;   // [0] uncertain count, [1] ready, [2] inexact
+  int32_t* counters;       // [0] uncertain count, [2] inexact, [4..5] dyn K (two parities), [8..11] running stats
   size_t bytes;
 };
 
-static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d) {
+static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int band) {
   Carver c(ws, ws_bytes);
   ConsLayout L{};
-  L.bf = c.take<__nv_bfloat16>((size_t)n * d);
-  L.norm = c.take<float>((size_t)n);
+  L.X = c.take<__nv_bfloat16>((size_t)n * d);
+  L.xnorm = c.take<float>((size_t)n);
+  L.Y = c.take<__nv_bfloat16>((size_t)n * d);
+  L.ynorm = c.take<float>((size_t)n);
   L.words_per_row = (n + kTcBN - 1) / kTcBN * (kTcBN / 32);
   L.mask = c.take<uint32_t>((size_t)n * L.words_per_row);
-  L.kept_words = (n + kScanRows - 1) / kScanRows * kScanWords;
-  L.kept = c.take<unsigned long long>((size_t)L.kept_words);
+  L.kept_words = (band / kScanRows + 1) * kScanWords;
+  L.kept[0] = c.take<unsigned long long>((size_t)L.kept_words);
+  L.kept[1] = c.take<unsigned long long>((size_t)L.kept_words);
   int64_t cap = 64 * n + (1 << 20);
   if (cap > 0x3fffffff) cap = 0x3fffffff;
   L.unc_cap = (int32_t)cap;
@@ -310,7 +410,7 @@ extern "C" {
 
 size_t hippo_consolidate_workspace_bytes(int64_t n, int32_t d) {
   if (n <= 2 || d <= 0) return 256;
-  return hippo::cons_layout(nullptr, 0, n, d).bytes;
+  return hippo::cons_layout(nullptr, 0, n, d, hippo::cons_band()).bytes;
 }
 
 hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float gamma, float band_exact,
@@ -329,18 +429,21 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
     HIPPO_CUDA(cudaGetLastError());
     return HIPPO_OK;
   }
-  ConsLayout L = cons_layout(ws, ws_bytes, n, d);
+  const int band = cons_band();
+  ConsLayout L = cons_layout(ws, ws_bytes, n, d, band);
   if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
     set_error("hippo_consolidate: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;
   }
   HIPPO_CUDA(cudaMemsetAsync(L.counters, 0, 64 * sizeof(int32_t), s));
-  st = hippo_bank_build(feats, HIPPO_F32, n, d, d, L.bf, L.norm, L.counters + 2, stream);
+  st = hippo_bank_build(feats, HIPPO_F32, n, d, d, L.X, L.xnorm, L.counters + 2, stream);
   if (st != HIPPO_OK) return st;
+  int32_t* dyn = L.counters + 4;
+  int32_t* stats = L.counters + 8;
 
   TcMaskArgs a{};
-  a.feats_bf16 = L.bf;
-  a.norm = L.norm;
+  a.feats_bf16 = L.Y;
+  a.norm = L.ynorm;
   a.n = n;
   a.d = d;
   a.gamma = gamma;
@@ -352,36 +455,52 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
   a.uncertain = L.unc;
   a.uncertain_count = L.counters + 0;
   a.uncertain_cap = L.unc_cap;
-  st = tc_mask_launch(a, s);
-  if (st != HIPPO_OK) return st;
 
-  recheck_kernel<<<sm_count() * 8, 256, 0, s>>>(feats, L.norm, d, gamma, L.unc, L.counters + 0, L.unc_cap,
-                                                 L.mask, L.words_per_row);
-  HIPPO_CUDA(cudaGetLastError());
-  const int scan_blocks = (int)((n + kScanRows - 1) / kScanRows);
-  HIPPO_CUDA(cudaMemsetAsync(L.kept, 0, (size_t)L.kept_words * sizeof(unsigned long long), s));
-  unsigned long long* dbg = nullptr;
-  if (getenv("HIPPO_SCAN_DEBUG")) cudaMalloc(&dbg, (size_t)scan_blocks * 64);
-  greedy_scan_kernel<<<scan_blocks, kScanThreads, 0, s>>>(L.mask, L.words_per_row, n, L.kept, dbg);
-  if (dbg) {
-    cudaStreamSynchronize(s);
-    std::vector<unsigned long long> h((size_t)scan_blocks * 8);
-    cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    cudaFree(dbg);
-    const unsigned long long t0 = h[0];
-    for (int i = 0; i < scan_blocks; ++i)
-      if (i < 6 || i % 16 == 0 || i > scan_blocks - 4)
-        fprintf(stderr, "[scan] blk %3d start %8.2f bulk_done %8.2f phaseA %8.2f (%llu rounds) preds %8.2f published %8.2f us  (rounds %llu, since prev publish %.2f)\n", i,
-                (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 5] - t0) / 1e3, h[i * 8 + 6], (h[i * 8 + 2] - t0) / 1e3, (h[i * 8 + 3] - t0) / 1e3, h[i * 8 + 4],
-                i ? (h[i * 8 + 3] - h[(i - 1) * 8 + 3]) / 1e3 : 0.0);
-  }
-  HIPPO_CUDA(cudaGetLastError());
-  compact_kernel<<<1, 1024, 0, s>>>(L.kept, L.kept_words, n, out_keep, out_count);
-  HIPPO_CUDA(cudaGetLastError());
-  if (out_stats) {
-    stats_kernel<<<1, 1, 0, s>>>(L.counters + 0, L.unc_cap, L.counters + 2, out_stats);
+  const int adv_grid = sm_count() * 4;
+  const int scan_grid = band / kScanRows + 1;
+  const bool dbg_on = getenv("HIPPO_SCAN_DEBUG") != nullptr;
+  int par = 1;                      // dyn[par] = K before the band being finished
+  int64_t prev_r0 = 0;
+  int prev_rows = 0;
+  int iband = 0;
+  for (int64_t r0 = 0;; r0 += band, ++iband) {
+    const int rows = (int)(r0 < n ? (n - r0 < band ? n - r0 : band) : 0);
+    // kept-words: band i publishes into kept[i & 1]; the advance after band i-1 reads kept[(i-1) & 1] and clears kept[i & 1]
+    cons_advance_kernel<<<adv_grid, kAdvThreads, 0, s>>>(L.X, L.xnorm, d, L.Y, L.ynorm, out_keep,
+                                                         L.kept[(iband + 1) & 1], L.kept[iband & 1], L.kept_words, dyn,
+                                                         par, prev_r0, prev_rows, r0, rows, L.counters + 0, L.unc_cap,
+                                                         stats);
     HIPPO_CUDA(cudaGetLastError());
+    par ^= 1;                       // dyn[par] = K before this band
+    if (rows == 0) break;
+    a.dyn_k = dyn + par;
+    a.band_rows = rows;
+    st = tc_mask_launch(a, s);
+    if (st != HIPPO_OK) return st;
+    recheck_kernel<<<sm_count() * 8, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
+                                                   L.unc_cap, L.mask, L.words_per_row);
+    HIPPO_CUDA(cudaGetLastError());
+    unsigned long long* dbg = nullptr;
+    if (dbg_on) { cudaMalloc(&dbg, (size_t)scan_grid * 64); cudaMemset(dbg, 0, (size_t)scan_grid * 64); }
+    greedy_scan_kernel<<<scan_grid, kScanThreads, 0, s>>>(L.mask, L.words_per_row, dyn + par, rows, L.kept[iband & 1], dbg);
+    HIPPO_CUDA(cudaGetLastError());
+    if (dbg) {
+      cudaStreamSynchronize(s);
+      std::vector<unsigned long long> h((size_t)scan_grid * 8);
+      cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+      cudaFree(dbg);
+      const unsigned long long t0 = h[0];
+      for (int i = 0; i < scan_grid; ++i)
+        if (iband % 8 == 0 && h[i * 8 + 3])
+          fprintf(stderr, "[scan] band %d blk %2d start %7.2f bulk_done %7.2f phaseA %7.2f (%llu rounds) preds %7.2f published %7.2f us (rounds %llu)\n",
+                  iband, i, (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 5] - t0) / 1e3, h[i * 8 + 6],
+                  (h[i * 8 + 2] - t0) / 1e3, (h[i * 8 + 3] - t0) / 1e3, h[i * 8 + 4]);
+    }
+    prev_r0 = r0;
+    prev_rows = rows;
   }
+  cons_finish_kernel<<<1, 1, 0, s>>>(dyn, par, L.counters + 2, stats, out_count, out_stats);
+  HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
 

@@ -67,6 +67,8 @@ struct TcParams {
                                  // slow path (per warp), [3] cycles epilogue warps wait for accumulators, [4] epilogue tiles x warps,
                                  // [5] cycles the MMA thread waits for TMEM, [6] cycles it waits for operands
   // mask
+  const int32_t* dyn_k;   // banded consolidation: rows [0, *dyn_k) of B are final (kept); A rows [*dyn_k, *dyn_k + band_rows)
+  int band_rows, i0;      // i0: first 256-row block to compute (set on the device from *dyn_k)
   float gamma, band_exact, band_inexact;
   const int32_t* inexact;
   uint32_t* mask;
@@ -91,6 +93,24 @@ __device__ __forceinline__ void decode_unit(const TcParams& p, int unit, int& m_
     m_base = 2 * (unit - split * p.m_pairs);
     t0 = split * p.tiles_per_split;
     t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+  } else if (p.dyn_k != nullptr) {
+    // banded consolidation: row blocks [i0, n_tiles) against column tiles t <= I, column tile slowest so the
+    // pairs running concurrently share it.  h row blocks; t < i0: all of them, then the triangle of the band.
+    const int h = p.n_tiles - p.i0;
+    const int rect = p.i0 * h;
+    int I;
+    if (unit < rect) {
+      t0 = unit / h;
+      I = p.i0 + (unit - t0 * h);
+    } else {
+      int r = unit - rect, j = 0;
+      while (r >= h - j) { r -= h - j; ++j; }
+      t0 = p.i0 + j;
+      I = t0 + r;
+    }
+    t1 = t0 + 1;
+    m_base = 2 * I;
+    split = 0;
   } else {
     // lower triangle of 256 x 256 blocks (t <= I), enumerated in BANDS of kBand row blocks: inside a band the
     // column tile t varies slowest, so the pairs running concurrently share ~9 column tiles and the band's
@@ -224,8 +244,20 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const TcParams p) {
+              const TcParams p_in) {
   extern __shared__ unsigned char smem_raw[];
+  TcParams p = p_in;
+  if constexpr (EPI == EPI_MASK) {
+    if (p_in.dyn_k != nullptr) {
+      // the extent of this launch depends on how many rows the previous bands kept: read it here, no host sync
+      const int kfinal = *p_in.dyn_k;
+      p.n = (int64_t)kfinal + p_in.band_rows;
+      p.i0 = 2 * (kfinal / 512);               // whole 512-row scan blocks are recomputed
+      p.n_tiles = (int)((p.n + kTcBN - 1) / kTcBN);
+      const int h = p.n_tiles - p.i0;
+      p.units = p.i0 * h + h * (h + 1) / 2;
+    }
+  }
   // identical carve-up in both CTAs of the pair: the MMA and the multicast commits address the peer's
   // shared memory by the same offsets (pointer arithmetic on the __shared__ array keeps LDS/STS)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -768,6 +800,8 @@ hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   p.uncertain = a.uncertain;
   p.uncertain_count = a.uncertain_count;
   p.uncertain_cap = a.uncertain_cap;
+  p.dyn_k = a.dyn_k;
+  p.band_rows = a.band_rows;
   p.debug = debug_flags();
   return launch<EPI_MASK>(tmA, tmB, p, s);
 }

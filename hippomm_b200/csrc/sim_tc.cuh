@@ -45,6 +45,8 @@ struct TcMaskArgs {
   uint2* uncertain;          // (i, j) pairs within the band
   int32_t* uncertain_count;  // zero-initialised by the caller
   int32_t uncertain_cap;
+  const int32_t* dyn_k;      // banded mode (consolidate.cu): device count of final rows; null = whole triangle
+  int band_rows;             // rows of this band (A rows [*dyn_k, *dyn_k + band_rows))
 };
 hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s);
 
