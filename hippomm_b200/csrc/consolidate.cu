@@ -31,7 +31,7 @@
 
 namespace hippo {
 
-constexpr int kConsBandDefault = 4096;
+constexpr int kConsBandDefault = 8192;
 
 // ---- 3. exact re-evaluation of near-threshold pairs ---------------------------------
 // One warp per pair (i, j) of Y rows.  The rows are looked up in the caller's fp32 matrix through yidx,
@@ -282,6 +282,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
 // to dyn[par_in ^ 1], and the next band's rows [next_r0, next_r0 + next_rows) are copied to Y[K', ...).
 // Everything is read from X (the bf16 image of the caller's rows), never from Y, so the compaction cannot
 // trample rows it still needs.  Every CTA recomputes the (short) prefix over the kept-words on its own.
+// one bf16 row, 16 bytes per lane and step, four loads in flight per lane
+__device__ __forceinline__ void copy_row(const uint4* __restrict__ sp, uint4* __restrict__ dp, int nvec, int lane) {
+  int v = lane;
+  for (; v + 96 < nvec; v += 128) {
+    const uint4 a = ldg_stream(sp + v), b = ldg_stream(sp + v + 32), c = ldg_stream(sp + v + 64), e = ldg_stream(sp + v + 96);
+    dp[v] = a; dp[v + 32] = b; dp[v + 64] = c; dp[v + 96] = e;
+  }
+  for (; v < nvec; v += 32) dp[v] = ldg_stream(sp + v);
+}
+
 constexpr int kAdvThreads = 256;
 constexpr int kAdvMaxWords = 1024;   // band of at most 32k - 512 rows
 
@@ -305,10 +315,18 @@ __global__ void __launch_bounds__(kAdvThreads) cons_advance_kernel(
     s_bits[w] = bits;
   }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int w = 0; w < nwords; ++w) { s_pref[w] = acc; acc += __popc(s_bits[w]); }
-    s_pref[nwords] = acc;
+  if (tid < 32) {      // exclusive prefix of the popcounts: one warp, 32 words per step
+    int carry = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+      const int w = w0 + tid;
+      const int c = w < nwords ? __popc(s_bits[w]) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+      if (w < nwords) s_pref[w] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (tid == 0) s_pref[nwords] = carry;
   }
   __syncthreads();
   const int added = s_pref[nwords];
@@ -324,17 +342,13 @@ __global__ void __launch_bounds__(kAdvThreads) cons_advance_kernel(
     if (!((bits >> (pos & 31)) & 1u)) continue;
     const int rank = s_pref[pos >> 5] + __popc(bits & ((1u << (pos & 31)) - 1u));
     const int64_t src = prev_r0 + t, dst = (int64_t)K + rank;
-    const uint4* sp = reinterpret_cast<const uint4*>(X + src * d);
-    uint4* dp = reinterpret_cast<uint4*>(Y + dst * d);
-    for (int v = lane; v < vec_per_row; v += 32) dp[v] = sp[v];
+    copy_row(reinterpret_cast<const uint4*>(X + src * d), reinterpret_cast<uint4*>(Y + dst * d), vec_per_row, lane);
     if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
   }
   // next band
   for (int64_t t = warp; t < next_rows; t += nwarps) {
     const int64_t src = next_r0 + t, dst = (int64_t)K2 + t;
-    const uint4* sp = reinterpret_cast<const uint4*>(X + src * d);
-    uint4* dp = reinterpret_cast<uint4*>(Y + dst * d);
-    for (int v = lane; v < vec_per_row; v += 32) dp[v] = sp[v];
+    copy_row(reinterpret_cast<const uint4*>(X + src * d), reinterpret_cast<uint4*>(Y + dst * d), vec_per_row, lane);
     if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
   }
   // the next band's hand-off words, the uncertain-pair list, the running statistics
@@ -456,7 +470,7 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
   a.uncertain_count = L.counters + 0;
   a.uncertain_cap = L.unc_cap;
 
-  const int adv_grid = sm_count() * 4;
+  const int adv_grid = sm_count() * 8;
   const int scan_grid = band / kScanRows + 1;
   const bool dbg_on = getenv("HIPPO_SCAN_DEBUG") != nullptr;
   int par = 1;                      // dyn[par] = K before the band being finished
@@ -477,7 +491,7 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
     a.band_rows = rows;
     st = tc_mask_launch(a, s);
     if (st != HIPPO_OK) return st;
-    recheck_kernel<<<sm_count() * 8, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
+    recheck_kernel<<<sm_count() * 4, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
                                                    L.unc_cap, L.mask, L.words_per_row);
     HIPPO_CUDA(cudaGetLastError());
     unsigned long long* dbg = nullptr;

@@ -164,3 +164,43 @@ def test_scan_adversarial_structures(cuda_device, kind):
         assert len(ref) == n
     else:
         assert list(ref) == [0]
+
+
+@pytest.mark.parametrize("band", [512, 1024])
+@pytest.mark.parametrize("kind", ["videolike", "chain", "all_kept", "zero_rows"])
+def test_small_bands_many_handoffs(cuda_device, monkeypatch, band, kind):
+    """The banded pipeline with bands far smaller than the input: kept rows are compacted between bands at
+    offsets that are not multiples of the 256-row tiles / 512-row scan blocks, and the first scan block of
+    every band re-resolves rows that are already final."""
+    from hippomm_b200 import select_key_frames, synth
+
+    monkeypatch.setenv("HIPPO_CONS_BAND", str(band))
+    rng = np.random.default_rng(5 + band)
+    n, d = 3333, 1024
+    if kind == "videolike":
+        feats = synth.videolike_features(41, 134, 25)[:n]
+    elif kind == "chain":
+        c, s = 0.93, np.sqrt(1 - 0.93 ** 2)
+        v = rng.standard_normal(d)
+        v /= np.linalg.norm(v)
+        rows = []
+        for _ in range(n):
+            rows.append(v.copy())
+            u = rng.standard_normal(d)
+            u -= u.dot(v) * v
+            u /= np.linalg.norm(u)
+            v = c * v + s * u
+        feats = np.asarray(rows, dtype=np.float32)
+    elif kind == "all_kept":
+        feats = rng.standard_normal((n, d)).astype(np.float32)
+    else:
+        feats = synth.videolike_features(43, 134, 25)[:n].copy()
+        feats[[7, 600, 601, 2049]] = 0.0            # zero-norm rows: NaN similarity, never kept (hm:960)
+    for gamma in (0.9, 0.95):
+        ref, moat = O.select_key_frames_blocked(feats, gamma, block=900, with_moat=True)
+        kept = select_key_frames(feats, None, gamma)
+        if moat > 1e-6:
+            assert np.array_equal(kept, ref), f"{kind} band={band} gamma={gamma}: {len(kept)} vs {len(ref)} kept"
+        else:
+            ok, why = O.greedy_valid_under_tolerance(feats, kept, gamma)
+            assert ok, why
