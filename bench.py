@@ -407,6 +407,30 @@ def run_gpu_arm(args):
         line["extra"] = run_extras(bank, q_dev, peaks, device, lib)
     elif rank == 0:
         line["cpu_baseline"] = None
+    if world > 1 and not args.no_extra:
+        # config 5: single-query latency over the sharded bank, one query in flight -- GEMV over this rank's shard,
+        # then the exchange + merge; every rank issues the same calls, rank 0 reports its own clock
+        lat = []
+        for i in range(3 + 200):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, _, kk = bank.search_keys(q_dev[i % NQ].reshape(1, DIM), k, "single")
+            exchange_merge(kk)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                lat.append(e0.elapsed_time(e1))
+        lat.sort()
+        bytes_ = n_local * DIM * 2 + n_local * 4
+        if rank == 0:
+            line["extra"] = {"sharded_single_query": {
+                "latency_ms": {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99) - 1], "min": lat[0],
+                               "max": lat[-1], "samples": len(lat)},
+                "queries_per_s": 1e3 / lat[len(lat) // 2],
+                "roofline": {"bound": "hbm", "achieved": bytes_ / (lat[len(lat) // 2] * 1e-3) / 1e9, "peak": peaks["hbm"],
+                             "unit": "GB/s per GPU", "frac": bytes_ / (lat[len(lat) // 2] * 1e-3) / 1e9 / peaks["hbm"]},
+                "config": f"1 query top-{k} over {n_total} rows sharded over {world} GPUs ({n_local} rows per GPU), "
+                          f"exchange {exchange}"}}
     barrier()
     if rank == 0:
         emit(line)

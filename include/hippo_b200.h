@@ -188,10 +188,13 @@ hippo_status hippo_recall_windows(const int64_t* seg_idx, const float* seg_score
  * Greedy redundancy filter: row 0 is kept; row i is kept iff
  * cos(row i, row j) < gamma for every kept j < i (hm:958-961).  gamma is
  * compared in fp32 like NumPy does for an fp32 matrix and a Python float.
- * The similarity contraction runs on tcgen05 over the strict lower triangle
- * only and leaves a bit matrix (never the fp32 matrix); pairs whose
- * tensor-core similarity is within `band` of gamma are re-evaluated from the
- * fp32 rows before the greedy scan.
+ * The rule only consults similarities against KEPT rows, so the rows are
+ * processed in bands: a band is contracted on tcgen05 against the rows kept so
+ * far (compacted) and against itself (strict lower triangle), leaving bits
+ * (never the fp32 matrix); pairs whose tensor-core similarity is within `band`
+ * of gamma are re-evaluated from the fp32 rows before the band's greedy scan.
+ * The whole call is asynchronous: how many rows are final is read from device
+ * memory by the next band's kernels.  Decisions equal the full-matrix rule.
  *   feats      [n, d] fp32 rows (time-ordered), row stride d, d % 64 == 0
  *   out_keep   [n] int64 kept row numbers ascending (first *out_count valid)
  *   out_count  int32* (device)

@@ -16,6 +16,6 @@ except Exception as e:
     print("   parse failed", e); print(open("gpurun_out/bench_${name}.err").read()[-1500:])
 PY
 }
-run strong${N}_p2p HIPPO_EXCHANGE=p2p --no-extra
+run strong${N}_p2p HIPPO_EXCHANGE=p2p
 run strong${N}_nccl HIPPO_EXCHANGE=nccl --no-extra
 run weak${N}_p2p HIPPO_EXCHANGE=p2p --no-extra --bank-rows $((10000000 * N))
