@@ -28,13 +28,73 @@ __device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r)
   return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
 }
 
-// grid (blocks_per_frame, nf).  3-channel fast path: a warp takes 32 groups of 16 pixels per step = 1536
-// contiguous BGR bytes, loaded as three fully coalesced 512-byte rows into the warp's shared-memory slot, then
-// every lane picks up its own 48 bytes (conflict-free: 12-word stride) and stores 16 gray bytes, coalesced.
+// 3-channel fast path (frames whose pixel count is a multiple of 16, no row padding): persistent warps loop over
+// (frame, 512-pixel slice) items.  A warp takes 32 groups of 16 pixels per item = 1536 contiguous BGR bytes,
+// loaded as three fully coalesced 512-byte rows into the warp's shared-memory slot, then every lane picks up
+// its own 48 bytes (conflict-free: 12-word stride) and stores 16 gray bytes, coalesced.
+__global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __restrict__ frames, int64_t npix,
+                                                              int nf, uint8_t* __restrict__ gray,
+                                                              int2* __restrict__ minmax) {
+  __shared__ uint4 s_stage[8][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ngroups = npix / 16;
+  const int64_t wpf = (ngroups + 31) / 32;                   // warp items per frame
+  const int64_t nitems = wpf * nf;
+  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < nitems; item += (int64_t)gridDim.x * 8) {
+    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;
+    const uint8_t* src = frames + f * npix * 3;
+    uint8_t* dst = gray + f * npix;
+    const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
+    const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
+    const uint4* p = reinterpret_cast<const uint4*>(src + g0 * 48);
+    uint4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) v[u] = ldg_stream(p + lane + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
+    __syncwarp();
+    uint32_t lo = 255, hi = 0;
+    if (lane < left) {
+      const uint4 a = s_stage[warp][3 * lane], b = s_stage[warp][3 * lane + 1], c = s_stage[warp][3 * lane + 2];
+      const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+      uint32_t out[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const int byte0 = (o * 4 + px) * 3;
+          uint32_t c3[3];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const int bi = byte0 + cc;
+            c3[cc] = (w[bi >> 2] >> ((bi & 3) * 8)) & 0xffu;
+          }
+          const uint32_t y = bgr2gray(c3[0], c3[1], c3[2]);
+          lo = min(lo, y); hi = max(hi, y);
+          packed |= y << (px * 8);
+        }
+        out[o] = packed;
+      }
+      *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(&minmax[f].x, (int)lo);
+      atomicMax(&minmax[f].y, (int)hi);
+    }
+  }
+}
+
+// General path (1 channel, odd sizes, padded rows): grid (blocks_per_frame, nf), one byte per thread and step.
 __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restrict__ frames, int64_t npix,
                                                           int w, int pitch, int ch, uint8_t* __restrict__ gray,
                                                           int2* __restrict__ minmax) {
-  __shared__ uint4 s_stage[8][96];
   __shared__ uint32_t s_lo[8], s_hi[8];
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -42,59 +102,17 @@ __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restr
   const int64_t gpix = npix / w * pitch;      // bytes of one padded gray frame
   uint8_t* dst = gray + (int64_t)f * gpix;
   uint32_t lo = 255, hi = 0;
-  const bool vec = pitch == w && (npix % 16 == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0);
-  if (ch == 3 && vec) {
-    const int64_t ngroups = npix / 16;
-    const int64_t nwarps = (int64_t)gridDim.x * 8;
-    for (int64_t g0 = ((int64_t)blockIdx.x * 8 + warp) * 32; g0 < ngroups; g0 += nwarps * 32) {
-      const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
-      const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
-      const uint4* p = reinterpret_cast<const uint4*>(src + g0 * 48);
-      uint4 v[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) v[u] = ldg_stream(p + lane + 32 * u);
-#pragma unroll
-      for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
-      __syncwarp();
-      if (lane < left) {
-        const uint4 a = s_stage[warp][3 * lane], b = s_stage[warp][3 * lane + 1], c = s_stage[warp][3 * lane + 2];
-        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-        uint32_t out[4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          uint32_t packed = 0;
-#pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const int byte0 = (o * 4 + px) * 3;
-            uint32_t c3[3];
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-              const int bi = byte0 + cc;
-              c3[cc] = (w[bi >> 2] >> ((bi & 3) * 8)) & 0xffu;
-            }
-            const uint32_t y = bgr2gray(c3[0], c3[1], c3[2]);
-            lo = min(lo, y); hi = max(hi, y);
-            packed |= y << (px * 8);
-          }
-          out[o] = packed;
-        }
-        *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
-      }
-      __syncwarp();
-    }
-  } else {
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < gpix;
-         o += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t r = o / pitch;
-      const int x = (int)(o - r * pitch);
-      if (x >= w) { dst[o] = 0; continue; }   // row padding: zero in both frames of a pair
-      const int64_t i = r * w + x;
-      uint32_t y;
-      if (ch == 3) y = bgr2gray(src[i * 3], src[i * 3 + 1], src[i * 3 + 2]);
-      else y = src[i];
-      dst[o] = (uint8_t)y;
-      lo = min(lo, y); hi = max(hi, y);
-    }
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < gpix;
+       o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = o / pitch;
+    const int x = (int)(o - r * pitch);
+    if (x >= w) { dst[o] = 0; continue; }   // row padding: zero in both frames of a pair
+    const int64_t i = r * w + x;
+    uint32_t y;
+    if (ch == 3) y = bgr2gray(src[i * 3], src[i * 3 + 1], src[i * 3 + 2]);
+    else y = src[i];
+    dst[o] = (uint8_t)y;
+    lo = min(lo, y); hi = max(hi, y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -314,7 +332,14 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   if (bpf < 1) bpf = 1;
   if (bpf > 64) bpf = 64;
   HIPPO_REQUIRE(nf <= 65535, "hippo_frame_pairs: at most 65535 frames per call");
-  gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
+  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
+  if (vec) {
+    const int64_t items = (npix / 16 + 31) / 32 * nf;
+    const int64_t want = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
+    gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.minmax);
+  } else {
+    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
+  }
   HIPPO_CUDA(cudaGetLastError());
   HIPPO_REQUIRE(npairs <= 65535, "hippo_frame_pairs: at most 65535 pairs per call");
   const int64_t nitems = (int64_t)npairs * L.nparts;
