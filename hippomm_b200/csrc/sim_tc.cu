@@ -246,18 +246,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const TcParams p_in) {
   extern __shared__ unsigned char smem_raw[];
-  TcParams p = p_in;
+  // the banded consolidation reads its extent from device memory (no host sync between bands); the search
+  // kernel keeps reading its parameters straight from the constant bank
+  TcParams pm;
   if constexpr (EPI == EPI_MASK) {
+    pm = p_in;
     if (p_in.dyn_k != nullptr) {
-      // the extent of this launch depends on how many rows the previous bands kept: read it here, no host sync
       const int kfinal = *p_in.dyn_k;
-      p.n = (int64_t)kfinal + p_in.band_rows;
-      p.i0 = 2 * (kfinal / 512);               // whole 512-row scan blocks are recomputed
-      p.n_tiles = (int)((p.n + kTcBN - 1) / kTcBN);
-      const int h = p.n_tiles - p.i0;
-      p.units = p.i0 * h + h * (h + 1) / 2;
+      pm.n = (int64_t)kfinal + p_in.band_rows;
+      pm.i0 = 2 * (kfinal / 512);               // whole 512-row scan blocks are recomputed
+      pm.n_tiles = (int)((pm.n + kTcBN - 1) / kTcBN);
+      const int h = pm.n_tiles - pm.i0;
+      pm.units = pm.i0 * h + h * (h + 1) / 2;
     }
   }
+  const TcParams& p = [&]() -> const TcParams& {
+    if constexpr (EPI == EPI_MASK) return pm; else return p_in;
+  }();
   // identical carve-up in both CTAs of the pair: the MMA and the multicast commits address the peer's
   // shared memory by the same offsets (pointer arithmetic on the __shared__ array keeps LDS/STS)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
