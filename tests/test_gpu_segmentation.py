@@ -30,9 +30,11 @@ def test_frame_ssim_matches_reference_outputs(cuda_device):
     assert np.array_equal(ssim < 0.95, g["frame_ssim_adjacent"] < 0.95)
 
 
-@pytest.mark.parametrize("h,w", [(7, 7), (8, 300), (57, 63), (64, 64), (119, 257), (224, 224), (180, 320), (70, 600)])
+@pytest.mark.parametrize("h,w", [(7, 7), (8, 300), (57, 63), (64, 64), (119, 257), (224, 224), (180, 320), (70, 600),
+                                 (62, 126), (63, 127), (9, 247), (118, 246), (61, 13)])
 def test_frame_pairs_shapes_against_oracle(cuda_device, h, w):
-    """Frame sizes around the band (56 rows) and column-chunk (250 columns) boundaries; SSIM and MSE."""
+    """Frame sizes around the band (56 window rows) and column-chunk (120 windows per warp) boundaries, widths
+    that are / are not multiples of 4 (row padding of the gray buffer) and of 16 (vectorised gray path)."""
     from hippomm_b200 import synth
 
     frames, _ = synth.frame_stream(h * 1000 + w, 6, h, w, min_scene=2, max_scene=3)
