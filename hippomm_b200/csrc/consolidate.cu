@@ -20,8 +20,8 @@
 //   3. recheck_kernel         pairs within `band` of gamma re-evaluated from the fp32 rows
 //   4. greedy_scan_kernel     row i kept iff no kept j < i has bit (i, j)           (hm:958-961)
 //
-// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed; the bit matrix is N^2/8 bytes
-// in the worst case (everything kept), and only the rows of the current band are ever live.
+// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed; the bit matrix holds the rows of
+// the current band only ((band + 1024) x N / 8 bytes: 115 MB at N = 100k).
 #include "common.cuh"
 #include "sim_tc.cuh"
 
@@ -43,7 +43,9 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
                                                       const int64_t* __restrict__ yidx,
                                                       float gamma, const uint2* __restrict__ pairs,
                                                       const int32_t* __restrict__ count, int32_t cap,
-                                                      uint32_t* __restrict__ mask, int64_t words_per_row) {
+                                                      uint32_t* __restrict__ mask, int64_t words_per_row,
+                                                      const int32_t* __restrict__ dyn_k) {
+  const int64_t row0 = (int64_t)(*dyn_k / 512) * 512;     // first row held by the band-local bit matrix
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
     acc = warp_sum(acc);
     if (lane == 0) {
       const bool bit = !(acc < (double)gamma);
-      uint32_t* w = mask + (int64_t)pr.x * words_per_row + (pr.y >> 5);
+      uint32_t* w = mask + ((int64_t)pr.x - row0) * words_per_row + (pr.y >> 5);
       const uint32_t m = 1u << (pr.y & 31);
       if (bit) atomicOr(w, m); else atomicAnd(w, ~m);
     }
@@ -141,9 +143,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
   const int b0 = kfinal / kScanRows;               // first block of this launch; blocks below it are all kept
   const int b = b0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t row = (int64_t)b * kScanRows + tid;
+  const int64_t row = (int64_t)blockIdx.x * kScanRows + tid;   // row of the band-local bit matrix (Y row - 512 b0)
   if ((int64_t)b * kScanRows >= n) return;         // nobody waits for a block past the end
-  const bool live = row < n;
+  const bool live = (int64_t)b * kScanRows + tid < n;
   auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = now();
 
@@ -387,7 +389,7 @@ struct ConsLayout {
   float* xnorm;
   __nv_bfloat16* Y;        // kept rows so far, compacted, followed by the current band
   float* ynorm;
-  uint32_t* mask;          // bit matrix in Y row numbers
+  uint32_t* mask;          // bit matrix of the current band: row = Y row - 512 (K / 512), columns in Y row numbers
   int64_t words_per_row;
   unsigned long long* kept[2];   // block-local tagged kept-words of the current / next band
   int kept_words;
@@ -405,7 +407,9 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int b
   L.Y = c.take<__nv_bfloat16>((size_t)n * d);
   L.ynorm = c.take<float>((size_t)n);
   L.words_per_row = (n + kTcBN - 1) / kTcBN * (kTcBN / 32);
-  L.mask = c.take<uint32_t>((size_t)n * L.words_per_row);
+  // the current band only: rows [512 (K / 512), K + band) rounded up to the 256-row blocks the contraction writes
+  const int64_t mask_rows = (n < (int64_t)band ? n : (int64_t)band) + 1024;
+  L.mask = c.take<uint32_t>((size_t)mask_rows * L.words_per_row);
   L.kept_words = (band / kScanRows + 1) * kScanWords;
   L.kept[0] = c.take<unsigned long long>((size_t)L.kept_words);
   L.kept[1] = c.take<unsigned long long>((size_t)L.kept_words);
@@ -492,7 +496,7 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
     st = tc_mask_launch(a, s);
     if (st != HIPPO_OK) return st;
     recheck_kernel<<<sm_count() * 4, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
-                                                   L.unc_cap, L.mask, L.words_per_row);
+                                                   L.unc_cap, L.mask, L.words_per_row, dyn + par);
     HIPPO_CUDA(cudaGetLastError());
     unsigned long long* dbg = nullptr;
     if (dbg_on) { cudaMalloc(&dbg, (size_t)scan_grid * 64); cudaMemset(dbg, 0, (size_t)scan_grid * 64); }

@@ -634,7 +634,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr[buf]);
       if constexpr (EPI == EPI_MASK) {
         if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(p.mask + arow * p.words_per_row + (int64_t)t * 8 + chalf * 4);
+          // banded mode: the bit matrix holds the current band only, rows numbered from the first row block computed
+          uint4* dst = reinterpret_cast<uint4*>(p.mask + (arow - (int64_t)p.i0 * kTcBN) * p.words_per_row + (int64_t)t * 8 + chalf * 4);
           *dst = make_uint4(words[0], words[1], words[2], words[3]);
         }
       } else {
