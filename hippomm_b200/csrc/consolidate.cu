@@ -413,8 +413,8 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int b
   L.kept_words = (band / kScanRows + 1) * kScanWords;
   L.kept[0] = c.take<unsigned long long>((size_t)L.kept_words);
   L.kept[1] = c.take<unsigned long long>((size_t)L.kept_words);
-  int64_t cap = 64 * n + (1 << 20);
-  if (cap > 0x3fffffff) cap = 0x3fffffff;
+  // the list is drained after every band
+  int64_t cap = 64 * ((n < (int64_t)band ? n : (int64_t)band) + 1024) + (1 << 20);
   L.unc_cap = (int32_t)cap;
   L.unc = c.take<uint2>((size_t)cap);
   L.counters = c.take<int32_t>(64);
