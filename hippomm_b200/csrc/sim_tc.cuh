@@ -15,9 +15,10 @@ struct TcTopkArgs {
   const float* bnorm;        // [n]
   int64_t n;
   int d;
-  const void* qbf16;         // [nq_pad, d] bf16 (nq_pad multiple of 128 not required; TMA zero-fills)
+  const void* qbf16;         // [nq_rows, d] bf16
   const float* qnorm;        // [nq]
   int nq;
+  int nq_rows;               // rows of qbf16 that exist (>= nq, zero rows beyond nq): extent of the TMA tensor map
   int k;
   int64_t row_base;
   const uint64_t* after_key; // [nq] or null

@@ -15,6 +15,7 @@ struct BatchedLayout {
   unsigned long long* counters;   // [8], first thing in the workspace so a profiling script can find it
   uint64_t* part;
   int splits;
+  int nq_pad;
   size_t bytes;
 };
 
@@ -22,7 +23,10 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   Carver c(ws, ws_bytes);
   BatchedLayout L{};
   L.counters = c.take<unsigned long long>(8);
-  L.qbf = c.take<__nv_bfloat16>((size_t)nq * d);
+  // padded with zero rows to whole 256-query blocks: TMA boxes that are partly or wholly out of bounds load at a
+  // fraction of the normal rate (8 queries took 0.75 ms where 256 took 0.41 ms on a 1M-row bank)
+  L.nq_pad = (nq + 2 * kTcBM - 1) / (2 * kTcBM) * (2 * kTcBM);
+  L.qbf = c.take<__nv_bfloat16>((size_t)L.nq_pad * d);
   L.qnorm = c.take<float>((size_t)nq);
   L.splits = tc_topk_splits(n, nq);
   const size_t units = (size_t)((nq + 2 * kTcBM - 1) / (2 * kTcBM)) * (size_t)L.splits;
@@ -72,6 +76,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   // queries -> bf16 + |a| (same pass the bank went through)
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
   if (st != HIPPO_OK) return st;
+  if (L.nq_pad > nq) HIPPO_CUDA(cudaMemsetAsync(L.qbf + (size_t)nq * d, 0, (size_t)(L.nq_pad - nq) * d * 2, s));
   TcTopkArgs a{};
   a.bank = bank;
   a.bnorm = norm;
@@ -80,6 +85,7 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   a.qbf16 = L.qbf;
   a.qnorm = L.qnorm;
   a.nq = nq;
+  a.nq_rows = L.nq_pad;
   a.k = k;
   a.row_base = row_base;
   a.after_key = after_key;
