@@ -139,6 +139,38 @@ def test_lattice_1m_planted_families(cuda_device):
         assert np.array_equal(rs.view(np.uint32), bs[qi].view(np.uint32))
 
 
+def test_lattice_10m_full_size(cuda_device):
+    """BASELINE config 4 at its full size (10M x 1024, 20.5 GB of bf16 rows, generated in place): every query's
+    top-10 is its planted family from BOTH kernels, the two kernels agree bit for bit, and the scores equal the
+    oracle's on the candidate rows.  The full 4,096-query batch of the config is the bench's parity gate."""
+    from hippomm_b200 import MemoryBank, synth
+
+    n, d, nq, seed = 10_000_000, 1024, 512, 4
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 << 30:
+        pytest.skip("needs 30 GB of free device memory")
+    bank = MemoryBank(n, d)
+    for r0 in range(0, n, 1 << 17):
+        m = min(1 << 17, n - r0)
+        bank.fill(r0, synth.lattice_rows_torch(seed, r0, m, d, n, cuda_device))
+    q, fam = synth.lattice_queries_np(seed, nq, d, n)
+    expect = synth.lattice_expected_topk(fam, n, 10)
+    bi, bs = _search(bank, q, 10, "batched")
+    assert np.array_equal(np.sort(bi, axis=1), expect)
+    assert np.all(np.diff(bs, axis=1) <= 0)
+    si, ss = _search(bank, q[:4], 10, "single")
+    assert np.array_equal(si, bi[:4])
+    assert np.array_equal(ss.view(np.uint32), bs[:4].view(np.uint32))
+    rows = np.unique(np.concatenate([expect[:4].reshape(-1), np.arange(9_990_000, 9_992_000)]))
+    sub = synth.lattice_rows_np(seed, rows, d, n)
+    for qi in range(4):
+        ri, rs = O.top_k_cosine_similarity(q[qi], sub, 10)
+        assert np.array_equal(rows[ri], bi[qi])
+        assert np.array_equal(rs.view(np.uint32), bs[qi].view(np.uint32))
+    del bank
+    torch.cuda.empty_cache()
+
+
 def test_row_base_and_merge(cuda_device, lib):
     """Two half-banks with row offsets + hippo_topk_merge == one full bank (the sharded-search merge, §8e)."""
     from hippomm_b200 import MemoryBank
