@@ -453,6 +453,40 @@ def _load_traffic():
 TRAFFIC = _load_traffic()
 
 
+def synth_stream_hour(device, nf=3600, h=224, w=224, sr=16000):
+    """Config 2's synthetic stream, generated on the device: piecewise-static scenes of 5-60 s (smooth field +
+    per-frame noise of 2 grey levels), int16 noise at -20 dBFS with silences of 0.6-3 s every 8-40 s."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(1)
+    frames = torch.empty((nf, h, w, 3), dtype=torch.uint8, device=device)
+    f0 = 0
+    while f0 < nf:
+        length = int(torch.randint(5, 61, (1,), generator=g, device=device).item())
+        m = min(length, nf - f0)
+        yy = torch.linspace(0, 6.28, h, device=device)[:, None, None]
+        xx = torch.linspace(0, 6.28, w, device=device)[None, :, None]
+        ph = torch.rand((1, 1, 3), generator=g, device=device) * 6.28
+        fr = torch.rand((2,), generator=g, device=device) * 3 + 0.5
+        field = 128 + 40 * torch.sin(fr[0] * xx + ph) + 40 * torch.cos(fr[1] * yy + ph)
+        noisy = field[None] + 2.0 * torch.randn((m, h, w, 3), generator=g, device=device)
+        frames[f0:f0 + m] = noisy.round().clamp(0, 255).to(torch.uint8)
+        f0 += m
+    ns = nf * sr
+    pcm = (torch.randn((ns, 1), generator=g, device=device) * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
+    t_s = 0
+    while True:
+        t_s += int(torch.randint(8, 41, (1,), generator=g, device=device).item())
+        if t_s >= nf - 3:
+            break
+        ln = int((0.6 + 2.4 * torch.rand((1,), generator=g, device=device).item()) * sr)
+        pcm[t_s * sr:t_s * sr + ln] = (pcm[t_s * sr:t_s * sr + ln].float() * 1e-3).round().to(torch.int16)
+        t_s += 3
+    ft = torch.arange(nf, dtype=torch.float64, device=device)
+    return frames, pcm, ft
+
+
 def run_extras(bank, q_dev, peaks, device, lib):
     """Secondary hot-path kernels at their BASELINE.json config sizes (1 GPU). Each: >= 3 warm-ups, CUDA events."""
     import torch
@@ -574,32 +608,8 @@ def run_extras(bank, q_dev, peaks, device, lib):
     # ---- segmentation, 1-hour stream: 3600 x 224 x 224 x 3 frames + 57.6M int16 samples (config 2) ----
     try:
         nf, h, w, sr = 3600, 224, 224, 16000
-        g = torch.Generator(device=device)
-        g.manual_seed(1)
-        frames = torch.empty((nf, h, w, 3), dtype=torch.uint8, device=device)
-        f0 = 0
-        while f0 < nf:
-            length = int(torch.randint(5, 61, (1,), generator=g, device=device).item())
-            m = min(length, nf - f0)
-            yy = torch.linspace(0, 6.28, h, device=device)[:, None, None]
-            xx = torch.linspace(0, 6.28, w, device=device)[None, :, None]
-            ph = torch.rand((1, 1, 3), generator=g, device=device) * 6.28
-            fr = torch.rand((2,), generator=g, device=device) * 3 + 0.5
-            field = 128 + 40 * torch.sin(fr[0] * xx + ph) + 40 * torch.cos(fr[1] * yy + ph)
-            noisy = field[None] + 2.0 * torch.randn((m, h, w, 3), generator=g, device=device)
-            frames[f0:f0 + m] = noisy.round().clamp(0, 255).to(torch.uint8)
-            f0 += m
+        frames, pcm, ft = synth_stream_hour(device, nf, h, w, sr)
         ns = nf * sr
-        pcm = (torch.randn((ns, 1), generator=g, device=device) * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
-        t_s = 0
-        while True:
-            t_s += int(torch.randint(8, 41, (1,), generator=g, device=device).item())
-            if t_s >= nf - 3:
-                break
-            ln = int((0.6 + 2.4 * torch.rand((1,), generator=g, device=device).item()) * sr)
-            pcm[t_s * sr:t_s * sr + ln] = (pcm[t_s * sr:t_s * sr + ln].float() * 1e-3).round().to(torch.int16)
-            t_s += 3
-        ft = torch.arange(nf, dtype=torch.float64, device=device)
         holder = {}
 
         def seg():

@@ -3,19 +3,24 @@
 // so that no product feeds a fused add the Python interpreter would have rounded).
 //
 // One CTA of 256 threads per stream.  The chain over segments is sequential (each boundary
-// anchors the next window), so the kernel is bound by the latency of ONE segment, which is kept
-// at about one global-memory round trip plus ONE barrier:
+// anchors the next window), so the kernel is bound by the latency of ONE segment -- the dependent
+// instruction chain of one thread plus one global-memory round trip and ONE barrier:
 //   * frame times and adjacent-pair SSIMs are staged in shared memory once (up to kStageFrames
 //     frames);
 //   * the window's frame range and the backward SSIM scan (hm:1045-1059) are one pass: every thread tests
 //     one frame from the previous window's start onwards (boundaries only move forward, no binary search),
 //     membership in [lo+1, hi] is decided from the frame's own and its predecessor's time, the latest pair
 //     below the threshold wins (atomicMax);
-//   * the audio scan (hm:1061-1077) evaluates 64 half-second windows per step, four lanes per window:
-//     a 30 s span has at most 59, so one step covers it.  The lanes split the window's pyramid terms
-//     (all loads independent, issued together) and reduce with shuffles; the first window in the
-//     reference's order that is below the threshold wins (atomicMin).  The threshold test runs in the
-//     power domain (no sqrt / log10 unless the mean is within 1e-12 of the threshold);
+//   * the audio scan (hm:1061-1077) looks at up to 64 half-second windows per step (a 30 s span has 59), ONE
+//     thread per window on warps 0-1 while warps 2-7 run the video scan.  A window is first classified from the
+//     512-sample level of the energy pyramid alone: the blocks that lie fully inside it bound its sum of squares
+//     from below, the blocks that cover it from above (~17 contiguous loads, no edge samples); a window whose
+//     bounds fall on the same side of the power threshold is decided.  Only when the EARLIEST candidate of a
+//     step is undecided (its mean within about half a dB of the threshold) the step is redone exactly: four
+//     lanes per window split the window's pyramid terms and edge samples (all loads independent, issued
+//     together) and reduce with shuffles.  The first window in the reference's order that is below the
+//     threshold wins (atomicMin).  The threshold test runs in the power domain (no sqrt / log10 unless the
+//     mean is within 1e-12 of the threshold);
 //   * the per-segment picks are triple-buffered in shared memory, so video, audio and the re-arming of
 //     the next segment's slots need no barrier between them.
 // The scalar state (current_start, current_end, optimal_end) is carried redundantly by all threads, which
@@ -31,6 +36,7 @@ namespace hippo {
 constexpr int kSegThreads = 256;                // every thread runs the scalar chain redundantly: few warps keep it cheap
 constexpr int kSegLanes = 4;                    // lanes per audio window
 constexpr int kSegWindows = kSegThreads / kSegLanes;   // 64 audio windows per step
+constexpr int kVidThreads = kSegThreads - kSegWindows; // threads 64..255 scan the frames while 0..63 classify windows
 constexpr int kSegBatch = 24;                   // pyramid terms a lane loads before it starts adding
 constexpr int kStageFrames = 6000;     // 2 x 6000 doubles = 96 KB of dynamic shared memory
 
@@ -95,6 +101,45 @@ __device__ __forceinline__ bool below_level(double sumsq, int64_t len, double db
   return level_db(sumsq, len) < db_thr;
 }
 
+// Classification of the window [s, e) (already clipped to the stream) from the 512-sample sums alone:
+// 0 = not below the threshold, 1 = below, 2 = undecided.  lower = blocks fully inside the window <= sum of squares
+// <= upper = blocks covering it; the last block of the stream holds the samples that exist, so it counts as inside
+// when the window ends with the stream.  The 1e-9 margins absorb the rounding of the block sums for float PCM
+// (int16-origin sums are exact) and keep the answer identical to below_level() of the exact sum, whose own
+// undecided band is 1e-12; an all-zero window (level -100) is "below" only for thresholds above -100 dB.
+__device__ __forceinline__ int window_class(const double* __restrict__ e512, int64_t s, int64_t e, int64_t ns,
+                                            double db_thr, double pow_thr) {
+  const int64_t len = e - s;
+  if (!(pow_thr > 0.0 && pow_thr < 1e300) || !(db_thr > -100.0)) return 2;
+  if (len <= 0) return 1;                                         // empty slice: level -100 (NumPy's mean is NaN)
+  const int64_t ba = s >> 9, bb = (e - 1) >> 9;                   // covering blocks [ba, bb]
+  const bool head_in = (s & 511) == 0, tail_in = (e & 511) == 0 || e == ns;
+  // every load below is independent of the others (batches of 16 inner blocks, predicated), so a half-second
+  // window at 16 kHz (at most 17 covering blocks) costs ONE memory round trip
+  const double head = e512[ba];
+  const double tail = e512[bb];
+  double inner = 0.0;
+  for (int64_t b0 = ba + 1; b0 < bb; b0 += 16) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (b0 + u < bb) ? e512[b0 + u] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) inner += (v[u] + v[u + 1]) + (v[u + 2] + v[u + 3]);
+  }
+  double lower, upper;
+  if (ba == bb) {
+    lower = (head_in && tail_in) ? head : 0.0;
+    upper = head;
+  } else {
+    lower = inner + (head_in ? head : 0.0) + (tail_in ? tail : 0.0);
+    upper = inner + head + tail;
+  }
+  const double bound = pow_thr * (double)len;
+  if (lower > bound * (1.0 + 1e-9)) return 0;
+  if (upper < bound * (1.0 - 1e-9)) return 1;
+  return 2;       // includes NaN sums
+}
+
 __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_stream_desc* __restrict__ streams,
                                                                  int nstreams, double max_dur, double min_dur,
                                                                  double ssim_thr, double db_thr,
@@ -104,7 +149,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   // thread 0 re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
   // left before the barrier of segment k - 1; first written in segment k + 1, after the barrier of segment k)
   __shared__ long long s_lo[3], s_vpick[3];
-  __shared__ int s_apick[3];
+  __shared__ int s_apick[3], s_amb[3];         // earliest window known to be below the threshold / earliest undecided one
   const int tid = threadIdx.x;
   const int si = blockIdx.x;
   if (si >= nstreams) return;
@@ -125,7 +170,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       ssim = s_stage + kStageFrames;
     }
   }
-  if (tid < 3) { s_lo[tid] = -1; s_vpick[tid] = -1; s_apick[tid] = 0x7fffffff; }
+  if (tid < 3) { s_lo[tid] = -1; s_vpick[tid] = -1; s_apick[tid] = 0x7fffffff; s_amb[tid] = 0x7fffffff; }
   __syncthreads();
 
   // hm:1027-1032
@@ -137,52 +182,57 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   const double pow_thr = pow(10.0, db_thr / 10.0);
   const int64_t w = has_audio ? (int64_t)(0.5 * sr) : 0;   // hm:1066; the host rejects w < 1 like range() does
   const bool scan_audio = has_audio && w >= 1;
+  const int vt = tid - kSegWindows;                  // video lane: threads 64..255
   int count = 0;
   bool overflow = false;
   int64_t hint = 0;                                  // first frame with t >= current_start so far
   double cs = 0.0;                                   // hm:1034
-  long long t_video = 0, t_audio = 0, t_bar = 0, t_tail = 0, t_a = 0, t_b = 0;
+  long long t_pre = 0, t_bar = 0, t_tail = 0, n_exact = 0;
   while (cs < total) {                               // hm:1036
     const long long c0 = dbg ? clock64() : 0;
     const int set = count % 3;
-    if (tid == 0) { const int nx = (count + 1) % 3; s_lo[nx] = -1; s_vpick[nx] = -1; s_apick[nx] = 0x7fffffff; }
+    if (tid == 0) {
+      const int nx = (count + 1) % 3;
+      s_lo[nx] = -1; s_vpick[nx] = -1; s_apick[nx] = 0x7fffffff; s_amb[nx] = 0x7fffffff;
+    }
     const double ce = py_min(cs + max_dur, total);   // hm:1038
     double opt = ce;                                 // hm:1041
     const int64_t s0 = (int64_t)(cs * sr);           // int() truncates toward zero
     const int64_t e0 = (int64_t)(ce * sr);
     const int64_t first = e0 - s0 - w;               // hm:1068: range(first, 0, -w)
 
-    // ---- video (hm:1045-1059).  The indices with cs <= t <= ce form one run [lo, hi] (frame_times is
-    // non-decreasing) and lo >= hint (boundaries only move forward).  The scan i = hi .. lo+1 stops at the first
-    // pair (frame i, frame i-1) with ssim[i-1] < threshold, i.e. the LARGEST such i: every thread tests one frame
-    // per step -- i is in the scan iff t[i-1] >= cs (i-1 >= lo) and t[i] <= ce (i <= hi) -- and atomicMax keeps it.
-    if (has_video) {
-      for (int64_t base = hint; base < nf; base += kSegThreads) {
-        const int64_t i = base + tid;
-        if (i < nf) {
-          const double t = ftimes[i];
-          const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
-          if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
-          if (ssim != nullptr && i > hint && tp >= cs && t <= ce && ssim[i - 1] < ssim_thr)   // NaN compares false, as in Python
-            atomicMax(&s_vpick[set], (long long)i);
+    if (tid >= kSegWindows) {
+      // ---- video (hm:1045-1059), threads 64..255.  The indices with cs <= t <= ce form one run [lo, hi]
+      // (frame_times is non-decreasing) and lo >= hint (boundaries only move forward).  The scan i = hi .. lo+1
+      // stops at the first pair (frame i, frame i-1) with ssim[i-1] < threshold, i.e. the LARGEST such i: every
+      // thread tests one frame per step -- i is in the scan iff t[i-1] >= cs (i-1 >= lo) and t[i] <= ce (i <= hi)
+      // -- and atomicMax keeps it.
+      if (has_video) {
+        for (int64_t base = hint; base < nf; base += kVidThreads) {
+          const int64_t i = base + vt;
+          if (i < nf) {
+            const double t = ftimes[i];
+            const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
+            if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
+            if (ssim != nullptr && i > hint && tp >= cs && t <= ce && ssim[i - 1] < ssim_thr)   // NaN compares false, as in Python
+              atomicMax(&s_vpick[set], (long long)i);
+          }
+          const int64_t last = base + kVidThreads - 1;
+          if (last >= nf - 1 || ftimes[last] > ce) break;                    // uniform: the run ends inside this step
         }
-        const int64_t last = base + kSegThreads - 1;
-        if (last >= nf - 1 || ftimes[last] > ce) break;                      // uniform: the run ends inside this step
       }
-    }
-    const long long c1 = dbg ? clock64() : 0;
-
-    // ---- audio (hm:1061-1077; runs second in the reference and overwrites the video boundary)
-    if (scan_audio) {
-      const int64_t i = first - (int64_t)(tid / kSegLanes) * w;   // four lanes per window
-      int64_t ws = 0, we = 0;
+    } else if (scan_audio) {
+      // ---- audio (hm:1061-1077; runs second in the reference and overwrites the video boundary), threads 0..63:
+      // one window per thread, classified from the 512-sample sums
+      const int64_t i = first - (int64_t)tid * w;
       if (i > 0) {
-        ws = s0 + i; we = ws + w;                    // audio_data[window_start:window_end] clips
+        int64_t ws = s0 + i, we = ws + w;            // audio_data[window_start:window_end] clips
         if (ws > S.ns) ws = S.ns;
         if (we > S.ns) we = S.ns;
+        const int cls = window_class(S.e512, ws, we, S.ns, db_thr, pow_thr);
+        if (cls == 1) atomicMin(&s_apick[set], tid);
+        else if (cls == 2) atomicMin(&s_amb[set], tid);
       }
-      const double ss = group_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & (kSegLanes - 1));
-      if (i > 0 && (tid & (kSegLanes - 1)) == 0 && below_level(ss, we - ws, db_thr, pow_thr)) atomicMin(&s_apick[set], tid / kSegLanes);
     }
     const long long c2 = dbg ? clock64() : 0;
     __syncthreads();
@@ -193,14 +243,14 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       hint = lo >= 0 ? lo : nf;
       if (pick >= 0) opt = ftimes[pick];             // hm:1057
     }
-    const long long c3a = dbg ? clock64() : 0;
     if (scan_audio) {
       int apick = s_apick[set];
+      const int amb = s_amb[set];
       int64_t base = first;
-      // further steps only when the span holds more than 64 windows (max_segment_duration > 32 s)
-      while (apick == 0x7fffffff && base - (int64_t)kSegWindows * w > 0) {
-        base -= (int64_t)kSegWindows * w;
-        __syncthreads();                              // everyone has read s_apick
+      // One exact step over the 64 windows below `base`, four lanes per window (every thread takes part).  The
+      // windows the classifier decided come out the same way, so s_apick needs no reset.
+      auto exact_step = [&]() -> int {
+        __syncthreads();                              // everyone has read s_apick / s_amb
         const int64_t i = base - (int64_t)(tid / kSegLanes) * w;
         int64_t ws = 0, we = 0;
         if (i > 0) {
@@ -211,7 +261,14 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
         const double ss = group_window_sumsq(S.pcm, S.pcm_dtype, S.nch, S.e16, S.e512, ws, we, tid & (kSegLanes - 1));
         if (i > 0 && (tid & (kSegLanes - 1)) == 0 && below_level(ss, we - ws, db_thr, pow_thr)) atomicMin(&s_apick[set], tid / kSegLanes);
         __syncthreads();
-        apick = s_apick[set];
+        ++n_exact;
+        return s_apick[set];
+      };
+      if (amb < apick) apick = exact_step();          // the earliest candidate is undecided
+      // further steps only when the span holds more than 64 windows (max_segment_duration > 32 s)
+      while (apick == 0x7fffffff && base - (int64_t)kSegWindows * w > 0) {
+        base -= (int64_t)kSegWindows * w;
+        apick = exact_step();
       }
       if (apick != 0x7fffffff) {
         const int64_t iw = base - (int64_t)apick * w;
@@ -219,7 +276,6 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       }
     }
 
-    const long long c3b = dbg ? clock64() : 0;
     // hm:1080-1084
     if (opt - cs < min_dur) opt = py_min(cs + min_dur, total);
 
@@ -231,10 +287,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     }
     ++count;
     cs = opt;                                        // hm:1111
-    if (dbg) { const long long c4 = clock64(); t_video += c1 - c0; t_audio += c2 - c1; t_bar += c3 - c2; t_tail += c4 - c3; t_a += c3a - c3; t_b += c3b - c3a; }
+    if (dbg) { const long long c4 = clock64(); t_pre += c2 - c0; t_bar += c3 - c2; t_tail += c4 - c3; }
   }
   if (tid == 0) *S.out_count = overflow ? -1 : count;
-  if (dbg && tid == 0 && si == 0) { dbg[0] = t_video; dbg[1] = t_audio; dbg[2] = t_bar; dbg[3] = t_tail; dbg[4] = t_a; dbg[5] = t_b; dbg[6] = count; }
+  if (dbg && tid == 0 && si == 0) { dbg[0] = t_pre; dbg[1] = t_bar; dbg[2] = t_tail; dbg[3] = n_exact; dbg[6] = count; }
 }
 
 }  // namespace hippo
@@ -261,8 +317,8 @@ extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* stream
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
     cudaFree(dbg);
-    fprintf(stderr, "[seg] %llu segments; cycles/segment: video %.0f audio %.0f barrier %.0f tail %.0f (reads %.0f, audio pick %.0f)\n", h[6],
-            (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+    fprintf(stderr, "[seg] %llu segments, %llu exact audio steps; cycles/segment (thread 0): scan %.0f barrier %.0f tail %.0f\n", h[6], h[3],
+            (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6]);
   }
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Development helper: segmentation of config 2's synthetic stream-hour only, timed per stage with CUDA events
+(gray + SSIM, audio pyramid, boundary state machine).  HIPPO_SEG_DEBUG=1 prints the boundary kernel's cycle split."""
+import hashlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device,  # noqa: E402
+                                       segment_boundaries_device)
+
+device = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+frames, pcm, ft = bench.synth_stream_hour(device)
+sr = 16000
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+ssim, mse = frame_pair_scores_device(frames, range_mode=0)
+pyr = audio_energy_device(pcm)
+out = segment_boundaries_device(ssim, ft, pcm, pyr, sr, 30.0, 10.0, 0.95, -40.0, 512)
+torch.cuda.synchronize()
+n = int(out[1].item())
+digest = hashlib.sha1(out[0][:n].cpu().numpy().tobytes() + ssim.cpu().numpy().tobytes()).hexdigest()[:16]
+dbg = os.environ.pop("HIPPO_SEG_DEBUG", None)      # the debug path synchronises: keep it out of the timings
+t_pairs = timed(lambda: frame_pair_scores_device(frames, range_mode=0))
+t_audio = timed(lambda: audio_energy_device(pcm))
+t_seg = timed(lambda: segment_boundaries_device(ssim, ft, pcm, pyr, sr, 30.0, 10.0, 0.95, -40.0, 512))
+
+
+def whole():
+    s, _ = frame_pair_scores_device(frames, range_mode=0)
+    p = audio_energy_device(pcm)
+    segment_boundaries_device(s, ft, pcm, p, sr, 30.0, 10.0, 0.95, -40.0, 512)
+
+
+t_all = timed(whole)
+print(f"[seg_only] segments {n} digest {digest}  frame pairs {t_pairs:.3f} ms  audio pyramid {t_audio:.3f} ms  "
+      f"boundaries {t_seg:.3f} ms  whole {t_all:.3f} ms")
+if dbg:
+    os.environ["HIPPO_SEG_DEBUG"] = dbg
+    segment_boundaries_device(ssim, ft, pcm, pyr, sr, 30.0, 10.0, 0.95, -40.0, 512)
+    torch.cuda.synchronize()
