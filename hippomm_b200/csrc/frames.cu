@@ -138,11 +138,29 @@ constexpr int kSsimWarps = kSsimThreads / 32;
 constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
 constexpr int kSsimBand = 56;                  // window rows per band
 
+// Packed fp32 pairs (sm_100 f32x2 arithmetic): two IEEE round-to-nearest results per instruction.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 | k); }
 
 // One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
 // squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
 // [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
+// (4 CTAs per SM at 64 registers measured 3% slower than 3 at 69)
 __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
     const uint8_t* __restrict__ gray, int h, int w, int pitch, const int32_t* __restrict__ pair_a,
     const int32_t* __restrict__ pair_b, const int2* __restrict__ minmax, int range_mode, int bh,
@@ -183,10 +201,12 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
 #pragma unroll
   for (int k = 0; k < 4; ++k) own[k] = lane < 30 && chunk * kSsimChunk + lane * 4 + k < out_cols;
 
-  int sp[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
+  // sliding 7-row column sums: sum x | sum y << 16, sum (x^2 + y^2) (the two variances only ever appear added), sum x y
+  int sp[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
   double acc = 0.0;
   unsigned long long sse = 0;
-  uint32_t sq = 0, cr = 0;                        // sum a^2 + b^2, sum a b of the rows owned for the squared error
+  uint32_t sqe = 0, cr = 0;                       // sum a^2 + b^2, sum a b of the rows owned for the squared error
+  const uint64_t c1s2 = pack_f32x2(c1s, c1s), c2s2 = pack_f32x2(c2s, c2s), two2 = pack_f32x2(2.f, 2.f);
 
   auto ldw = [&](const uint8_t* g, int r) -> uint32_t {   // callers pass r >= y0; rows past the frame read as zero
     return (col_ok && r < h) ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
@@ -198,8 +218,8 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
     const uint32_t noa = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(ga, r - 6) : 0u;
     const uint32_t nob = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(gb, r - 6) : 0u;
     if (sse_own && r < sse_r1) {
-      sq = __dp4a(wa, wa, sq); sq = __dp4a(wb, wb, sq); cr = __dp4a(wa, wb, cr);
-      if ((r & 63) == 63) { sse += (unsigned long long)sq - 2ull * cr; sq = 0; cr = 0; }   // 64 rows x 8 x 255^2 < 2^32
+      sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr);
+      if ((r & 63) == 63) { sse += (unsigned long long)sqe - 2ull * cr; sqe = 0; cr = 0; }   // 64 rows x 8 x 255^2 < 2^32
     }
     if (r < y0 + rows_in) {                       // warp-uniform
 #pragma unroll
@@ -208,15 +228,13 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
         const int ao = (int)byte_of(oa, k), bo = (int)byte_of(ob, k);
         const int da = an - ao, db = bn - bo;
         sp[k] += da + db * 65536;                 // sum x | sum y << 16: the running sums never go negative
-        sxx[k] += da * (an + ao);
-        syy[k] += db * (bn + bo);
+        sq[k] += da * (an + ao) + db * (bn + bo);
         sxy[k] += an * bn - ao * bo;
       }
       if (r >= y0 + 6) {
         // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
         // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
-        float s4 = 0.f;
-        int o_sp[4], o_xx[4], o_yy[4], o_xy[4];
+        int o_sp[4], o_sq[4], o_xy[4];
         auto horiz = [&](const int (&c)[4], int (&o)[4]) {
           // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
           const int C = c[0] + c[1] + c[2], D = C + c[3];
@@ -227,30 +245,41 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
           o[2] = o[1] + m0 - c[1];
           o[3] = o[2] + m1 - c[2];
         };
-        horiz(sp, o_sp); horiz(sxx, o_xx); horiz(syy, o_yy); horiz(sxy, o_xy);
+        horiz(sp, o_sp); horiz(sq, o_sq); horiz(sxy, o_xy);
+        float fu[4], fvs[4], fpxy[4], fvxy[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
           const int pxy = sx * sy;
           const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
-          const int vs = 49 * (o_xx[k] + o_yy[k]) - u;        // 48*49 (var_x + var_y), exact
-          const int vxy = 49 * o_xy[k] - pxy;                 // 48*49 cov_xy, exact
-          const float a1 = fmaf(2.f, (float)pxy, c1s);
-          const float a2 = fmaf(2.f, (float)vxy, c2s);
-          const float b1 = (float)u + c1s;
-          const float b2 = (float)vs + c2s;
-          const float den = b1 * b2;
-          float rcp;                                          // 1 ulp; 0 * inf (constant frames, R = 0) stays NaN like 0/0
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
-          const float sv = (a1 * a2) * rcp;
-          s4 += own[k] ? sv : 0.f;
+          fu[k] = (float)u;
+          fvs[k] = (float)(49 * o_sq[k] - u);                 // 48*49 (var_x + var_y), exact
+          fpxy[k] = (float)pxy;
+          fvxy[k] = (float)(49 * o_xy[k] - pxy);              // 48*49 cov_xy, exact
+        }
+        // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms)
+        float s4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          const uint64_t a1 = fma_f32x2(two2, pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
+          const uint64_t a2 = fma_f32x2(two2, pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
+          const uint64_t b1 = add_f32x2(pack_f32x2(fu[k], fu[k + 1]), c1s2);
+          const uint64_t b2 = add_f32x2(pack_f32x2(fvs[k], fvs[k + 1]), c2s2);
+          float d0, d1, r0, r1;
+          unpack_f32x2(mul_f32x2(b1, b2), d0, d1);
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));   // 1 ulp; 0 * inf (constant frames, R = 0) stays NaN like 0/0
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+          float v0, v1;
+          unpack_f32x2(mul_f32x2(mul_f32x2(a1, a2), pack_f32x2(r0, r1)), v0, v1);
+          s4 += own[k] ? v0 : 0.f;
+          s4 += own[k + 1] ? v1 : 0.f;
         }
         acc += (double)s4;
       }
     }
     wa = nwa; wb = nwb; oa = noa; ob = nob;
   }
-  sse += (unsigned long long)sq - 2ull * cr;
+  sse += (unsigned long long)sqe - 2ull * cr;
 
   acc = warp_sum(acc);
 #pragma unroll
