@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 
-_workspaces: dict[tuple[int, str], torch.Tensor] = {}
+_workspaces: dict[tuple[int, str, int], torch.Tensor] = {}
 _checked_devices: set[int] = set()
 
 
@@ -34,8 +34,11 @@ def stream_ptr() -> int:
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "default") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag); torch's caching allocator returns >=512 B aligned blocks."""
-    key = (device.index, tag)
+    """Grow-only scratch buffer per (device, tag, current stream): calls on different streams never share scratch
+    (the C ABI is reentrant across streams only under that condition); torch's caching allocator returns
+    >= 512 B aligned blocks and recycles a replaced buffer in stream order."""
+    with torch.cuda.device(device):
+        key = (device.index, tag, torch.cuda.current_stream().cuda_stream)
     buf = _workspaces.get(key)
     nbytes = max(int(nbytes), 256)
     if buf is None or buf.numel() < nbytes:
