@@ -108,35 +108,39 @@ __device__ __forceinline__ bool below_level(double sumsq, int64_t len, double db
 // (int16-origin sums are exact) and keep the answer identical to below_level() of the exact sum, whose own
 // undecided band is 1e-12; an all-zero window (level -100) is "below" only for thresholds above -100 dB.
 __device__ __forceinline__ int window_class(const double* __restrict__ e512, int64_t s, int64_t e, int64_t ns,
-                                            double db_thr, double pow_thr) {
+                                            int64_t w, double bound_w_lo, double bound_w_hi, double db_thr,
+                                            double pow_thr) {
   const int64_t len = e - s;
   if (!(pow_thr > 0.0 && pow_thr < 1e300) || !(db_thr > -100.0)) return 2;
   if (len <= 0) return 1;                                         // empty slice: level -100 (NumPy's mean is NaN)
   const int64_t ba = s >> 9, bb = (e - 1) >> 9;                   // covering blocks [ba, bb]
   const bool head_in = (s & 511) == 0, tail_in = (e & 511) == 0 || e == ns;
-  // every load below is independent of the others (batches of 16 inner blocks, predicated), so a half-second
-  // window at 16 kHz (at most 17 covering blocks) costs ONE memory round trip
-  const double head = e512[ba];
-  const double tail = e512[bb];
+  // every load below is independent of the others (batches of 16 inner blocks, predicated, immediate offsets), so
+  // a half-second window at 16 kHz (at most 17 covering blocks) costs ONE memory round trip
+  const double* p = e512 + ba;
+  const int nin = (int)(bb - ba) - 1;                             // inner blocks ba+1 .. bb-1
+  const double head = p[0];
+  const double tail = p[nin + 1 > 0 ? nin + 1 : 0];
   double inner = 0.0;
-  for (int64_t b0 = ba + 1; b0 < bb; b0 += 16) {
+  for (int u0 = 0; u0 < nin; u0 += 16) {
     double v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = (b0 + u < bb) ? e512[b0 + u] : 0.0;
-#pragma unroll
-    for (int u = 0; u < 16; u += 4) inner += (v[u] + v[u + 1]) + (v[u + 2] + v[u + 3]);
+    for (int u = 0; u < 16; ++u) v[u] = (u0 + u < nin) ? p[1 + u0 + u] : 0.0;
+    inner += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) +
+             (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
   }
   double lower, upper;
-  if (ba == bb) {
+  if (nin < 0) {                                                  // one covering block
     lower = (head_in && tail_in) ? head : 0.0;
     upper = head;
   } else {
     lower = inner + (head_in ? head : 0.0) + (tail_in ? tail : 0.0);
     upper = inner + head + tail;
   }
-  const double bound = pow_thr * (double)len;
-  if (lower > bound * (1.0 + 1e-9)) return 0;
-  if (upper < bound * (1.0 - 1e-9)) return 1;
+  double lo = bound_w_lo, hi = bound_w_hi;                        // pow_thr * w * (1 -+ 1e-9), hoisted by the caller
+  if (len != w) { const double bound = pow_thr * (double)len; lo = bound * (1.0 - 1e-9); hi = bound * (1.0 + 1e-9); }
+  if (lower > hi) return 0;
+  if (upper < lo) return 1;
   return 2;       // includes NaN sums
 }
 
@@ -146,9 +150,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
                                                                  unsigned long long* dbg) {
   extern __shared__ double s_stage[];          // [kStageFrames] frame times, [kStageFrames] ssim
   // per-segment results, triple-buffered so that ONE barrier per segment suffices: segment k uses set k % 3,
-  // thread 0 re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
+  // the last thread re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
   // left before the barrier of segment k - 1; first written in segment k + 1, after the barrier of segment k)
-  __shared__ long long s_lo[3], s_vpick[3];
+  __shared__ long long s_lo[3];
+  __shared__ int s_vpick[3];                   // latest pair below the threshold, as frame number - hint (-1 = none)
   __shared__ int s_apick[3], s_amb[3];         // earliest window known to be below the threshold / earliest undecided one
   const int tid = threadIdx.x;
   const int si = blockIdx.x;
@@ -163,10 +168,20 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   const double* ftimes = S.frame_times;
   const double* ssim = S.ssim;
   if (has_video && nf <= kStageFrames) {
-    for (int64_t i = tid; i < nf; i += kSegThreads) s_stage[i] = S.frame_times[i];
+    // eight independent loads in flight per thread: the staging is a handful of memory round trips, not nf / 256
+    auto stage = [&](const double* __restrict__ src, double* dst, int64_t cnt) {
+      for (int64_t i0 = tid; i0 < cnt; i0 += 8 * kSegThreads) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = i0 + u * kSegThreads < cnt ? src[i0 + u * kSegThreads] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (i0 + u * kSegThreads < cnt) dst[i0 + u * kSegThreads] = v[u];
+      }
+    };
+    stage(S.frame_times, s_stage, nf);
     ftimes = s_stage;
     if (S.ssim != nullptr) {
-      for (int64_t i = tid; i < nf - 1; i += kSegThreads) s_stage[kStageFrames + i] = S.ssim[i];
+      stage(S.ssim, s_stage + kStageFrames, nf - 1);
       ssim = s_stage + kStageFrames;
     }
   }
@@ -183,6 +198,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   const int64_t w = has_audio ? (int64_t)(0.5 * sr) : 0;   // hm:1066; the host rejects w < 1 like range() does
   const bool scan_audio = has_audio && w >= 1;
   const int vt = tid - kSegWindows;                  // video lane: threads 64..255
+  const double bound_w_lo = pow_thr * (double)w * (1.0 - 1e-9), bound_w_hi = pow_thr * (double)w * (1.0 + 1e-9);
   int count = 0;
   bool overflow = false;
   int64_t hint = 0;                                  // first frame with t >= current_start so far
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   while (cs < total) {                               // hm:1036
     const long long c0 = dbg ? clock64() : 0;
     const int set = count % 3;
-    if (tid == 0) {
+    if (tid == kSegThreads - 1) {                    // a thread of the video group: off the audio threads' critical path
       const int nx = (count + 1) % 3;
       s_lo[nx] = -1; s_vpick[nx] = -1; s_apick[nx] = 0x7fffffff; s_amb[nx] = 0x7fffffff;
     }
@@ -210,13 +226,16 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       if (has_video) {
         for (int64_t base = hint; base < nf; base += kVidThreads) {
           const int64_t i = base + vt;
+          int cand = -1;
           if (i < nf) {
             const double t = ftimes[i];
             const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
             if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
             if (ssim != nullptr && i > hint && tp >= cs && t <= ce && ssim[i - 1] < ssim_thr)   // NaN compares false, as in Python
-              atomicMax(&s_vpick[set], (long long)i);
+              cand = (int)(i - hint);         // a run of more than 2^31 frames inside one window does not exist
           }
+          const int wmax = __reduce_max_sync(0xffffffffu, cand);             // one shared-memory atomic per warp
+          if ((tid & 31) == 0 && wmax >= 0) atomicMax(&s_vpick[set], wmax);
           const int64_t last = base + kVidThreads - 1;
           if (last >= nf - 1 || ftimes[last] > ce) break;                    // uniform: the run ends inside this step
         }
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
         int64_t ws = s0 + i, we = ws + w;            // audio_data[window_start:window_end] clips
         if (ws > S.ns) ws = S.ns;
         if (we > S.ns) we = S.ns;
-        const int cls = window_class(S.e512, ws, we, S.ns, db_thr, pow_thr);
+        const int cls = window_class(S.e512, ws, we, S.ns, w, bound_w_lo, bound_w_hi, db_thr, pow_thr);
         if (cls == 1) atomicMin(&s_apick[set], tid);
         else if (cls == 2) atomicMin(&s_amb[set], tid);
       }
@@ -239,9 +258,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     const long long c3 = dbg ? clock64() : 0;
 
     if (has_video) {
-      const long long lo = s_lo[set], pick = s_vpick[set];
+      const long long lo = s_lo[set];
+      const int pick = s_vpick[set];
+      if (pick >= 0) opt = ftimes[hint + pick];      // hm:1057 (the pick is relative to this segment's hint)
       hint = lo >= 0 ? lo : nf;
-      if (pick >= 0) opt = ftimes[pick];             // hm:1057
     }
     if (scan_audio) {
       int apick = s_apick[set];
