@@ -215,8 +215,12 @@ def segment_boundaries_batch_device(streams, max_segment_duration: float, min_se
     descs = (_lib.StreamDesc * n)()
     for i, (ssim, ft, pcm, pyr, sr) in enumerate(streams):
         _fill_stream_desc(descs[i], ssim, ft, pcm, pyr, sr, bounds[i], counts[i:i + 1], max_segments)
-    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(descs), ctypes.sizeof(descs)), dtype=np.uint8).copy()
-    desc_dev = torch.from_numpy(raw).to(dev)
+    # descriptor table through pinned memory, asynchronously: the call never blocks the host (torch's pinned-memory
+    # cache keeps the staging block alive until the copy has run)
+    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(descs), ctypes.sizeof(descs)), dtype=np.uint8)
+    staged = torch.empty((raw.size,), dtype=torch.uint8, pin_memory=True)
+    staged.numpy()[:] = raw
+    desc_dev = staged.to(dev, non_blocking=True)
     with torch.cuda.device(dev):
         _lib.check(lib.hippo_segment_boundaries(
             desc_dev.data_ptr(), n, float(max_segment_duration), float(min_segment_duration),
