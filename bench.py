@@ -500,7 +500,7 @@ def run_extras(bank, q_dev, peaks, device, lib):
     from hippomm_b200 import _cuda, _lib
     from hippomm_b200.consolidation import select_key_frames_device
     from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device,
-                                           segment_boundaries_batch_device, segment_boundaries_device)
+                                           pattern_separation_batch_device, segment_boundaries_device)
 
     extra = {}
 
@@ -695,22 +695,21 @@ def run_extras(bank, q_dev, peaks, device, lib):
         # per stream exceed L2, so every replay streams from HBM.
         nstreams = 32
 
-        def seg_batch():
-            sts = []
-            for _ in range(nstreams):
-                ssim_b, _ = frame_pair_scores_device(frames, range_mode=0)
-                sts.append((ssim_b, ft, pcm, audio_energy_device(pcm), sr))
-            holder["batch"] = segment_boundaries_batch_device(sts, 30.0, 10.0, 0.95, -40.0, 512)
+        def seg_batch(lanes):
+            holder["batch"] = pattern_separation_batch_device([(frames, ft, pcm, sr)] * nstreams, 30.0, 10.0, 0.95,
+                                                              -40.0, 512, lanes=lanes)
 
-        t_batch = time_fn(seg_batch, 2, warm=1)
+        t_batch1 = time_fn(lambda: seg_batch(1), 2, warm=1)
+        t_batch = time_fn(lambda: seg_batch(2), 2, warm=1)
         same = bool(torch.equal(holder["batch"][0][5, :10], holder["out"][0][:10]))
         extra["segmentation_32_streams"] = {
             "ms_per_stream_hour": t_batch * 1e3 / nstreams, "stream_hours_per_s": nstreams / t_batch,
-            "matches_single_stream": same,
+            "ms_per_stream_hour_one_lane": t_batch1 * 1e3 / nstreams, "matches_single_stream": same,
             "roofline": {"bound": "hbm", "achieved": bytes_ * nstreams / t_batch / 1e9, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": bytes_ * nstreams / t_batch / 1e9 / peaks["hbm"],
                          "note": "the SSIM kernel is integer-issue bound, not HBM bound (DESIGN.md 4.4)"},
-            "config": f"{nstreams} stream-hours per batch, one boundary launch for all",
+            "config": f"{nstreams} stream-hours per batch: per-stream kernels on two alternating CUDA streams (gray "
+                      "conversion of one stream under the SSIM kernel of another), one boundary launch for all",
         }
         log(f"[extra] segmentation batch of {nstreams}: {t_batch * 1e3 / nstreams:.2f} ms per stream-hour")
     except Exception as e:

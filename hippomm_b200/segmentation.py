@@ -59,9 +59,10 @@ def _load_frames(video_frames: Sequence) -> np.ndarray:
 
 
 def frame_pair_scores_device(frames: torch.Tensor, pair_a: Optional[torch.Tensor] = None,
-                             pair_b: Optional[torch.Tensor] = None, range_mode: int = 0):
+                             pair_b: Optional[torch.Tensor] = None, range_mode: int = 0, out=None):
     """frames uint8 [n, h, w, ch] on the device -> (ssim fp64 [np], mse fp64 [np]) device tensors.
-    Without explicit pairs, pair p is (frame p+1, frame p), the order hm:1052-1056 scans them."""
+    Without explicit pairs, pair p is (frame p+1, frame p), the order hm:1052-1056 scans them.
+    `out` = (ssim, mse) contiguous fp64 tensors of at least np elements to write into."""
     lib = _lib.load()
     dev = _cuda.require_device(frames.device)
     if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_contiguous():
@@ -74,8 +75,14 @@ def frame_pair_scores_device(frames: torch.Tensor, pair_a: Optional[torch.Tensor
         pa = pair_a.to(dev, torch.int32).contiguous()
         pb = pair_b.to(dev, torch.int32).contiguous()
         npairs = pa.numel()
-    ssim = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
-    mse = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
+    if out is not None:
+        ssim, mse = out
+        for t in (ssim, mse):
+            if t.dtype != torch.float64 or not t.is_contiguous() or t.numel() < npairs or t.device != dev:
+                raise ValueError("out tensors must be contiguous fp64 device tensors of at least npairs elements")
+    else:
+        ssim = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
+        mse = torch.empty((max(npairs, 1),), dtype=torch.float64, device=dev)
     if npairs > 0:
         with torch.cuda.device(dev):
             ws_bytes = lib.hippo_frame_pairs_workspace_bytes(n, h, w, npairs)
@@ -226,6 +233,55 @@ def segment_boundaries_batch_device(streams, max_segment_duration: float, min_se
             desc_dev.data_ptr(), n, float(max_segment_duration), float(min_segment_duration),
             float(frame_similarity_threshold), float(audio_silence_threshold), _cuda.stream_ptr()))
     return bounds, counts
+
+
+def pattern_separation_batch_device(streams, max_segment_duration: float, min_segment_duration: float,
+                                    frame_similarity_threshold: float, audio_silence_threshold: float,
+                                    max_segments: int, lanes: int = 2):
+    """Temporal pattern separation of several independent streams resident on the device.
+
+    `streams`: list of (frames uint8 [nf, h, w, ch] or None, frame_times fp64 [nf] or None, pcm [ns, nch] or None,
+    sample_rate).  The per-stream kernels (gray + SSIM, audio pyramid) of consecutive streams are issued on `lanes`
+    alternating CUDA streams, so the HBM-bound gray conversion of one stream overlaps the issue-bound SSIM kernel of
+    another; ONE boundary launch (one CTA per stream) follows on the caller's stream.  Scratch is per CUDA stream
+    (`_cuda.workspace`), results are the same as stream-by-stream calls.
+    Returns (bounds fp64 [n, max_segments, 2], counts int32 [n])."""
+    if not streams:
+        raise ValueError("no streams")
+    ref = next(t for st in streams for t in (st[0], st[2]) if t is not None)
+    dev = _cuda.require_device(ref.device)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        side = _side_streams(dev, max(1, int(lanes)))
+        for sd in side:
+            sd.wait_stream(main)
+        prepared = []
+        for i, (frames, ft, pcm, sr) in enumerate(streams):
+            sd = side[i % len(side)]
+            with torch.cuda.stream(sd):
+                ssim = pyr = None
+                if frames is not None and frames.shape[0] > 1:
+                    ssim, _ = frame_pair_scores_device(frames, range_mode=0)
+                    ssim.record_stream(main)
+                if pcm is not None:
+                    pyr = audio_energy_device(pcm)
+                    pyr[0].record_stream(main)
+                    pyr[1].record_stream(main)
+            prepared.append((ssim, ft, pcm, pyr, sr))
+        for sd in side:
+            main.wait_stream(sd)
+        return segment_boundaries_batch_device(prepared, max_segment_duration, min_segment_duration,
+                                               frame_similarity_threshold, audio_silence_threshold, max_segments)
+
+
+_side: dict = {}
+
+
+def _side_streams(dev: torch.device, n: int):
+    pool = _side.setdefault(dev.index, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],

@@ -191,3 +191,73 @@ def test_batched_streams_match_single_stream_calls(cuda_device):
         c = int(c1.item())
         assert c > 0 and int(counts[i].item()) == c
         assert torch.equal(bounds[i, :c], b1[:c])
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_pattern_separation_batch_on_alternating_cuda_streams(cuda_device, lanes):
+    """Five streams of different shapes through pattern_separation_batch_device (per-stream kernels on `lanes`
+    alternating CUDA streams with per-stream scratch, one boundary launch) == the stream-by-stream calls, twice in a
+    row (the second call re-uses scratch and side streams)."""
+    from hippomm_b200 import synth
+    from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device,
+                                           pattern_separation_batch_device, segment_boundaries_device)
+
+    sr = 16000
+    inputs, want = [], []
+    for seed, (nsec, hw, video, audio) in enumerate([(150, (48, 64), True, True), (95, None, False, True),
+                                                     (120, (64, 48), True, False), (200, (56, 56), True, True),
+                                                     (61, (32, 40), True, True)]):
+        fd = ft = pcm = None
+        if video:
+            frames, _ = synth.frame_stream(30 + seed, nsec, hw[0], hw[1], min_scene=5, max_scene=25)
+            fd = torch.from_numpy(frames).to(cuda_device)
+            ft = torch.arange(nsec, dtype=torch.float64, device=cuda_device)
+        if audio:
+            pcm = torch.from_numpy(synth.audio_stream_int16(40 + seed, nsec * sr).reshape(-1, 1)).to(cuda_device)
+        inputs.append((fd, ft, pcm, sr if audio else None))
+        ssim = frame_pair_scores_device(fd, range_mode=0)[0] if video else None
+        pyr = audio_energy_device(pcm) if audio else None
+        b1, c1 = segment_boundaries_device(ssim, ft, pcm, pyr, sr if audio else None, 30.0, 10.0, 0.95, -40.0, 64)
+        torch.cuda.synchronize()
+        want.append(b1[: int(c1.item())].clone())
+    for _ in range(2):
+        bounds, counts = pattern_separation_batch_device(inputs, 30.0, 10.0, 0.95, -40.0, 64, lanes=lanes)
+        torch.cuda.synchronize()
+        for i, w in enumerate(want):
+            assert int(counts[i].item()) == len(w) > 0
+            assert torch.equal(bounds[i, : len(w)], w)
+
+
+@pytest.mark.parametrize("sr,dtype,nch", [(16000, "i16", 1), (8000, "i16", 1), (22050, "f32", 1), (44100, "i16", 2),
+                                          (16000, "f64", 1), (11025, "i16", 1)])
+def test_audio_scan_near_the_threshold(cuda_device, sr, dtype, nch):
+    """Audio-only streams whose level hovers around the -40 dB threshold in quarter-second pieces (0.5x .. 3x the
+    threshold amplitude, including 0.99x / 1.01x): most windows cannot be decided from the 512-sample bounds, so
+    both the block-sum classifier and the exact four-lane evaluation are exercised, at sample rates whose
+    half-second window is / is not a multiple of the 512- and 16-sample blocks.  Boundaries must equal the oracle's."""
+    from hippomm_b200 import segment_sequence
+
+    rng = np.random.default_rng(sr + nch)
+    nsec = 100
+    scales = np.array([3.0, 1.1, 1.01, 1.0, 0.99, 0.9, 0.5, 0.0]) * 0.01
+    probs = [0.30, 0.20, 0.20, 0.10, 0.10, 0.05, 0.03, 0.02]
+    piece = sr // 4
+    parts = []
+    for _ in range(nsec * 4):
+        amp = rng.choice(scales, p=probs)
+        parts.append(rng.standard_normal((piece, nch)) * amp)
+    x = np.concatenate(parts)[: nsec * sr - 37]          # ragged end
+    if dtype == "i16":
+        k = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+        given, seen = k, k.astype(np.float64) / 32768.0
+    elif dtype == "f32":
+        given = x.astype(np.float32)
+        seen = given.astype(np.float64)
+    else:
+        given = seen = x
+    for thresholds in ({}, {"max_segment_duration": 45.0, "min_segment_duration": 3.0}):
+        segs = segment_sequence(None, None, given, sr, **thresholds)
+        want = O.segment_boundaries(None, None, seen, sr, **thresholds)
+        assert [(s.start_time, s.end_time) for s in segs] == want
+        assert len(want) > 3
+
