@@ -552,6 +552,50 @@ def run_extras(bank, q_dev, peaks, device, lib):
     extra["single_query_search"]["latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99) - 1],
                                                   "min": lat[0], "max": lat[-1], "samples": len(lat)}
 
+    # ---- config 1 (the reference's own CPU-sized case) through the drop-in API: host arrays in, host arrays out ----
+    try:
+        import hippomm_b200 as hb
+        from hippomm_b200 import synth as _synth
+        from oracle import hippo_oracle as O
+
+        bank_h = _synth.videolike_features(20250417, 40, 50)              # 2,000 x 1024 fp32, 40 scenes x 50 frames
+        rng = np.random.default_rng(20250418)
+        js = rng.integers(0, len(bank_h), size=64)
+        qs = (bank_h[js] + np.float32(0.3) * rng.standard_normal((64, DIM)).astype(np.float32)).astype(np.float32)
+
+        def wall(fn, reps):
+            fn()
+            t1 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t1) / reps
+
+        def search_all(fn):
+            return lambda: [fn(qs[i], bank_h, 5) for i in range(64)]
+
+        t_ref = wall(search_all(O.top_k_cosine_similarity), 2) / 64
+        hb.set_bank_cache(0)
+        t_cold = wall(search_all(hb.top_k_cosine_similarity), 2) / 64      # bank uploaded + rebuilt on every call
+        hb.set_bank_cache(4)
+        t_warm = wall(search_all(hb.top_k_cosine_similarity), 2) / 64      # install(cache_banks=True): bank resident
+        hb.set_bank_cache(0)
+        same = all(np.array_equal(hb.top_k_cosine_similarity(qs[i], bank_h, 5)[0],
+                                  O.top_k_cosine_similarity(qs[i], bank_h, 5)[0]) for i in range(64))
+        t_kref = wall(lambda: O.select_key_frames(bank_h, None, 0.9), 2)
+        t_kgpu = wall(lambda: hb.select_key_frames(bank_h, None, 0.9), 3)
+        same_k = bool(np.array_equal(hb.select_key_frames(bank_h, None, 0.9), O.select_key_frames(bank_h, None, 0.9)))
+        extra["config1_dropin_host_arrays"] = {
+            "rows": int(len(bank_h)), "search_ms_per_call": {"cpu_port": t_ref * 1e3, "gpu_upload_every_call": t_cold * 1e3,
+                                                             "gpu_bank_cached": t_warm * 1e3},
+            "select_key_frames_ms": {"cpu_port": t_kref * 1e3, "gpu": t_kgpu * 1e3},
+            "identical_top5_rows": bool(same), "identical_kept_rows": same_k, "cores": os.cpu_count() or 1,
+            "note": "wall clock around the reference-signature calls (NumPy in, NumPy out); the GPU numbers include "
+                    "the 8 MB host-to-device copy of the feature array unless the bank is cached"}
+        log(f"[extra] config 1 drop-in: search {t_ref * 1e3:.2f} ms (CPU port) / {t_cold * 1e3:.2f} ms (GPU, upload per call) / "
+            f"{t_warm * 1e3:.2f} ms (GPU, cached bank); key frames {t_kref * 1e3:.0f} ms (CPU port) / {t_kgpu * 1e3:.1f} ms (GPU)")
+    except Exception as e:  # pragma: no cover
+        extra["config1_dropin_host_arrays"] = {"error": repr(e)}
+
     # ---- consolidation, 100k x 1024 video-like rows (config 3) ----
     try:
         n_scenes, fps = 2000, 50
