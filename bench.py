@@ -579,8 +579,17 @@ def run_extras(bank, q_dev, peaks, device, lib):
         hb.set_bank_cache(4)
         t_warm = wall(search_all(hb.top_k_cosine_similarity), 2) / 64      # install(cache_banks=True): bank resident
         hb.set_bank_cache(0)
-        same = all(np.array_equal(hb.top_k_cosine_similarity(qs[i], bank_h, 5)[0],
-                                  O.top_k_cosine_similarity(qs[i], bank_h, 5)[0]) for i in range(64))
+        # parity rule of SURVEY 8d: scores within 1e-3; rows may swap only inside a band of scores closer than that
+        # (neighbouring frames of a scene score within 1e-4 of each other, and the bank is held in bf16)
+        nrm = np.linalg.norm(bank_h, axis=1)
+        identical, worst, in_rule = 0, 0.0, True
+        for i in range(64):
+            gi, gs = hb.top_k_cosine_similarity(qs[i], bank_h, 5)
+            ri, rs = O.top_k_cosine_similarity(qs[i], bank_h, 5)
+            identical += int(np.array_equal(gi, ri))
+            worst = max(worst, float(np.max(np.abs(gs - rs))))
+            true = (bank_h[gi] @ qs[i]) / (nrm[gi] * np.linalg.norm(qs[i]))
+            in_rule = in_rule and bool(np.all(true >= rs[-1] - 1e-3)) and bool(np.all(np.abs(gs - rs) <= 1e-3))
         t_kref = wall(lambda: O.select_key_frames(bank_h, None, 0.9), 2)
         t_kgpu = wall(lambda: hb.select_key_frames(bank_h, None, 0.9), 3)
         same_k = bool(np.array_equal(hb.select_key_frames(bank_h, None, 0.9), O.select_key_frames(bank_h, None, 0.9)))
@@ -588,7 +597,8 @@ def run_extras(bank, q_dev, peaks, device, lib):
             "rows": int(len(bank_h)), "search_ms_per_call": {"cpu_port": t_ref * 1e3, "gpu_upload_every_call": t_cold * 1e3,
                                                              "gpu_bank_cached": t_warm * 1e3},
             "select_key_frames_ms": {"cpu_port": t_kref * 1e3, "gpu": t_kgpu * 1e3},
-            "identical_top5_rows": bool(same), "identical_kept_rows": same_k, "cores": os.cpu_count() or 1,
+            "top5_identical_queries": f"{identical}/64", "top5_max_abs_score_diff": worst,
+            "top5_within_parity_rule": in_rule, "identical_kept_rows": same_k, "cores": os.cpu_count() or 1,
             "note": "wall clock around the reference-signature calls (NumPy in, NumPy out); the GPU numbers include "
                     "the 8 MB host-to-device copy of the feature array unless the bank is cached"}
         log(f"[extra] config 1 drop-in: search {t_ref * 1e3:.2f} ms (CPU port) / {t_cold * 1e3:.2f} ms (GPU, upload per call) / "

@@ -21,6 +21,7 @@
 //                        prefixes.  Issue-bound (integer ALU), not HBM-bound: see DESIGN.md.
 //   ssim_finalize_kernel: ordered sum of the warp partials -> mean SSIM, MSE
 #include "common.cuh"
+#include <type_traits>
 
 namespace hippo {
 
@@ -160,8 +161,8 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_p
 // One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
 // squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
 // [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
-// (4 CTAs per SM at 64 registers measured 3% slower than 3 at 69)
-__global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
+// three CTAs per SM (at most 80 registers); four at 64 registers measured 3% slower
+__global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_kernel(
     const uint8_t* __restrict__ gray, int h, int w, int pitch, const int32_t* __restrict__ pair_a,
     const int32_t* __restrict__ pair_b, const int2* __restrict__ minmax, int range_mode, int bh,
     int nbands, int nchunks, int64_t nitems, double* __restrict__ part_ssim,
@@ -208,76 +209,101 @@ __global__ void __launch_bounds__(kSsimThreads, 2) ssim_pair_kernel(
   uint32_t sqe = 0, cr = 0;                       // sum a^2 + b^2, sum a b of the rows owned for the squared error
   const uint64_t c1s2 = pack_f32x2(c1s, c1s), c2s2 = pack_f32x2(c2s, c2s), two2 = pack_f32x2(2.f, 2.f);
 
-  auto ldw = [&](const uint8_t* g, int r) -> uint32_t {   // callers pass r >= y0; rows past the frame read as zero
-    return (col_ok && r < h) ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
+  // One row step.  kFull: the row completes a 7-row window (horizontal sums + ratio) and the row that leaves the
+  // window is fetched for the next step; kSse: this warp owns the row for the squared error.  The phases below
+  // call it with compile-time flags, so the steady state carries no per-row predicates: the only data-dependent
+  // address is the next row, clamped to the frame (its value is dead in the last step of a frame's last band).
+  static_assert(kSsimBand + 6 <= 64, "sqe / cr hold at most 64 rows x 4 bytes x 2 x 255^2 < 2^32 without a flush");
+  auto ldrow = [&](const uint8_t* g, int r) -> uint32_t {
+    return col_ok ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
   };
-  uint32_t wa = ldw(ga, y0), wb = ldw(gb, y0), oa = 0, ob = 0;
-  for (int r = y0; r < rend; ++r) {
-    // next row's words: issued now, used in the next iteration
-    const uint32_t nwa = ldw(ga, r + 1), nwb = ldw(gb, r + 1);
-    const uint32_t noa = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(ga, r - 6) : 0u;
-    const uint32_t nob = (r + 1 >= y0 + 7 && r + 1 < y0 + rows_in) ? ldw(gb, r - 6) : 0u;
-    if (sse_own && r < sse_r1) {
-      sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr);
-      if ((r & 63) == 63) { sse += (unsigned long long)sqe - 2ull * cr; sqe = 0; cr = 0; }   // 64 rows x 8 x 255^2 < 2^32
+  uint32_t wa = 0, wb = 0, oa = 0, ob = 0;
+  auto row_step = [&](int r, auto full_tag, auto sse_tag) {
+    constexpr bool kFull = decltype(full_tag)::value, kSse = decltype(sse_tag)::value;
+    // next row's words (and the row leaving the window): issued now, used in the next step
+    const int rn = min(r + 1, h - 1);
+    const uint32_t nwa = ldrow(ga, rn), nwb = ldrow(gb, rn);
+    uint32_t noa = 0, nob = 0;
+    if constexpr (kFull) { noa = ldrow(ga, r - 6); nob = ldrow(gb, r - 6); }
+    if constexpr (kSse) {
+      if (sse_own) { sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr); }
     }
-    if (r < y0 + rows_in) {                       // warp-uniform
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int an = (int)byte_of(wa, k), bn = (int)byte_of(wb, k);
+      const int ao = (int)byte_of(oa, k), bo = (int)byte_of(ob, k);
+      const int da = an - ao, db = bn - bo;
+      sp[k] += da + db * 65536;                 // sum x | sum y << 16: the running sums never go negative
+      sq[k] += da * (an + ao) + db * (bn + bo);
+      sxy[k] += an * bn - ao * bo;
+    }
+    if constexpr (kFull) {
+      // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
+      // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
+      int o_sp[4], o_sq[4], o_xy[4];
+      auto horiz = [&](const int (&c)[4], int (&o)[4]) {
+        // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
+        const int C = c[0] + c[1] + c[2], D = C + c[3];
+        const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c[3], 1);
+        const int m0 = __shfl_down_sync(0xffffffffu, c[0], 2), m1 = __shfl_down_sync(0xffffffffu, c[1], 2);
+        o[0] = D + C1n;
+        o[1] = o[0] + n3 - c[0];
+        o[2] = o[1] + m0 - c[1];
+        o[3] = o[2] + m1 - c[2];
+      };
+      horiz(sp, o_sp); horiz(sq, o_sq); horiz(sxy, o_xy);
+      float fu[4], fvs[4], fpxy[4], fvxy[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int an = (int)byte_of(wa, k), bn = (int)byte_of(wb, k);
-        const int ao = (int)byte_of(oa, k), bo = (int)byte_of(ob, k);
-        const int da = an - ao, db = bn - bo;
-        sp[k] += da + db * 65536;                 // sum x | sum y << 16: the running sums never go negative
-        sq[k] += da * (an + ao) + db * (bn + bo);
-        sxy[k] += an * bn - ao * bo;
+        const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
+        const int pxy = sx * sy;
+        const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
+        fu[k] = (float)u;
+        fvs[k] = (float)(49 * o_sq[k] - u);                 // 48*49 (var_x + var_y), exact
+        fpxy[k] = (float)pxy;
+        fvxy[k] = (float)(49 * o_xy[k] - pxy);              // 48*49 cov_xy, exact
       }
-      if (r >= y0 + 6) {
-        // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
-        // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
-        int o_sp[4], o_sq[4], o_xy[4];
-        auto horiz = [&](const int (&c)[4], int (&o)[4]) {
-          // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
-          const int C = c[0] + c[1] + c[2], D = C + c[3];
-          const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c[3], 1);
-          const int m0 = __shfl_down_sync(0xffffffffu, c[0], 2), m1 = __shfl_down_sync(0xffffffffu, c[1], 2);
-          o[0] = D + C1n;
-          o[1] = o[0] + n3 - c[0];
-          o[2] = o[1] + m0 - c[1];
-          o[3] = o[2] + m1 - c[2];
-        };
-        horiz(sp, o_sp); horiz(sq, o_sq); horiz(sxy, o_xy);
-        float fu[4], fvs[4], fpxy[4], fvxy[4];
+      // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms)
+      float s4 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
-          const int pxy = sx * sy;
-          const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
-          fu[k] = (float)u;
-          fvs[k] = (float)(49 * o_sq[k] - u);                 // 48*49 (var_x + var_y), exact
-          fpxy[k] = (float)pxy;
-          fvxy[k] = (float)(49 * o_xy[k] - pxy);              // 48*49 cov_xy, exact
-        }
-        // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms)
-        float s4 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; k += 2) {
-          const uint64_t a1 = fma_f32x2(two2, pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
-          const uint64_t a2 = fma_f32x2(two2, pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
-          const uint64_t b1 = add_f32x2(pack_f32x2(fu[k], fu[k + 1]), c1s2);
-          const uint64_t b2 = add_f32x2(pack_f32x2(fvs[k], fvs[k + 1]), c2s2);
-          float d0, d1, r0, r1;
-          unpack_f32x2(mul_f32x2(b1, b2), d0, d1);
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));   // 1 ulp; 0 * inf (constant frames, R = 0) stays NaN like 0/0
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
-          float v0, v1;
-          unpack_f32x2(mul_f32x2(mul_f32x2(a1, a2), pack_f32x2(r0, r1)), v0, v1);
-          s4 += own[k] ? v0 : 0.f;
-          s4 += own[k + 1] ? v1 : 0.f;
-        }
-        acc += (double)s4;
+      for (int k = 0; k < 4; k += 2) {
+        const uint64_t a1 = fma_f32x2(two2, pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
+        const uint64_t a2 = fma_f32x2(two2, pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
+        const uint64_t b1 = add_f32x2(pack_f32x2(fu[k], fu[k + 1]), c1s2);
+        const uint64_t b2 = add_f32x2(pack_f32x2(fvs[k], fvs[k + 1]), c2s2);
+        float d0, d1, r0, r1;
+        unpack_f32x2(mul_f32x2(b1, b2), d0, d1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));   // 1 ulp; 0 * inf (constant frames, R = 0) stays NaN like 0/0
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+        float v0, v1;
+        unpack_f32x2(mul_f32x2(mul_f32x2(a1, a2), pack_f32x2(r0, r1)), v0, v1);
+        s4 += own[k] ? v0 : 0.f;
+        s4 += own[k + 1] ? v1 : 0.f;
       }
+      acc += (double)s4;
     }
     wa = nwa; wb = nwb; oa = noa; ob = nob;
+  };
+  using T = std::true_type;
+  using F = std::false_type;
+  if (rows_in > 0) {
+    // rows [y0, y0+6) fill the window; [y0+6, sse_end) are complete rows this warp also owns for the squared
+    // error; [sse_end, y0+rows_in) are the six rows that belong to the next band's squared error
+    const int win_end = y0 + rows_in, sse_end = min(sse_r1, win_end);
+    wa = ldrow(ga, y0); wb = ldrow(gb, y0);
+    int r = y0;
+#pragma unroll 1
+    for (; r < y0 + 6; ++r) row_step(r, F{}, T{});
+#pragma unroll 1
+    for (; r < sse_end; ++r) row_step(r, T{}, T{});
+#pragma unroll 1
+    for (; r < win_end; ++r) row_step(r, T{}, F{});
+  } else if (sse_own) {
+    // a band without windows (frames lower than 7 rows): squared error only
+    for (int r = y0; r < sse_r1; ++r) {
+      const uint32_t xa = ldrow(ga, r), xb = ldrow(gb, r);
+      sqe = __dp4a(xa, xa, sqe); sqe = __dp4a(xb, xb, sqe); cr = __dp4a(xa, xb, cr);
+    }
   }
   sse += (unsigned long long)sqe - 2ull * cr;
 
