@@ -83,7 +83,7 @@ class PeerExchange:
         idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         score = torch.empty((nq, k), dtype=torch.float32, device=dev)
         key = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        self.epoch += 1
+        self.epoch = self.epoch % 0xFFFFFFFF + 1      # 1 .. 2^32 - 1, never 0 (the cleared state of the flags)
         with torch.cuda.device(dev):
             _lib.check(lib.hippo_topk_exchange_merge(
                 keys.contiguous().data_ptr(), nq, k_in, k, self.handle.buffer_ptrs_dev, self.nbytes, self.rank,
