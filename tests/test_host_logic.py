@@ -130,3 +130,64 @@ def test_install_rebinds_the_reference_symbols():
         hb.uninstall()
     assert (vo.top_k_cosine_similarity, hm.top_k_cosine_similarity, hm.HippocampalMemory._select_key_frames,
             hm.HippocampalMemory._segment_sequence, bp.compute_frame_difference) == orig
+
+
+def _window_class_model(e512, s, e, ns, w, db_thr):
+    """Host model of csrc/segment.cu:window_class -- the same block selection and the same margins, in NumPy fp64.
+    0 = not below the threshold, 1 = below, 2 = undecided (the kernel then evaluates the exact sum)."""
+    pow_thr = 10.0 ** (db_thr / 10.0)
+    if not (0.0 < pow_thr < 1e300) or not (db_thr > -100.0):
+        return 2
+    n = e - s
+    if n <= 0:
+        return 1
+    ba, bb = s >> 9, (e - 1) >> 9
+    head_in, tail_in = (s & 511) == 0, ((e & 511) == 0 or e == ns)
+    head, tail = e512[ba], e512[bb]
+    inner = float(np.sum(e512[ba + 1:bb])) if bb > ba + 1 else 0.0
+    if ba == bb:
+        lower, upper = (head if head_in and tail_in else 0.0), head
+    else:
+        lower = inner + (head if head_in else 0.0) + (tail if tail_in else 0.0)
+        upper = inner + head + tail
+    bound = pow_thr * float(n)
+    if lower > bound * (1.0 + 1e-9):
+        return 0
+    if upper < bound * (1.0 - 1e-9):
+        return 1
+    return 2
+
+
+def test_block_sum_classifier_never_contradicts_the_exact_level():
+    """The boundary kernel decides a half-second window from the 512-sample sums when it can (csrc/segment.cu).
+    Property: whenever the model of that classifier decides, the reference's own test `level < threshold`
+    (hm:993-1000, hm:1073) on the exact samples says the same -- for windows at every alignment, clipped at the end
+    of the stream, all-zero, louder and quieter than the threshold, and levels a hair away from it."""
+    rng = np.random.default_rng(7)
+    ns = 40_000 + 123
+    piece = 500
+    amps = rng.choice(np.array([0.0, 0.3, 0.9, 0.999, 1.0, 1.001, 1.1, 3.0]) * 0.01, size=ns // piece + 1)
+    x = (rng.standard_normal(ns) * np.repeat(amps, piece)[:ns])
+    k = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    x = k.astype(np.float64) / 32768.0                       # what the reference sees for pcm_s16le
+    sq = x * x
+    e512 = np.add.reduceat(sq, np.arange(0, ns, 512))        # exact for int16-origin samples
+    decided = undecided = 0
+    for w in (8000, 5512, 4000, 700, 512, 37):
+        for _ in range(400):
+            s = int(rng.integers(0, ns))
+            e = min(s + w, ns)
+            if rng.random() < 0.2:
+                s = (s >> 9) << 9                            # block-aligned starts
+            for db_thr in (-40.0, -36.5, -50.0):
+                cls = _window_class_model(e512, s, e, ns, w, db_thr)
+                exact = O.compute_audio_level(x[s:e]) < db_thr
+                if cls == 2:
+                    undecided += 1
+                else:
+                    decided += 1
+                    assert (cls == 1) == bool(exact), (s, e, w, db_thr, cls)
+    # the empty slice past the end of the stream: -100 dB, "below" for any threshold above -100
+    assert _window_class_model(e512, ns, ns, ns, 8000, -40.0) == 1 and O.compute_audio_level(x[ns:ns]) == -100
+    assert _window_class_model(e512, 0, 8000, ns, 8000, -100.0) == 2      # all-zero windows need the exact rule there
+    assert decided > 1000 and undecided > 50
