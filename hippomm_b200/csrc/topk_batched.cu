@@ -5,6 +5,13 @@
 
 namespace hippo {
 
+// topk_single.cu: the GEMV with two accumulators per row, for a batch too small for the tensor cores
+bool topk_few_supported(int d, int nq);
+size_t topk_few_part_elems(int nq, int k);
+hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, const float* q, int nq, int k,
+                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int64_t* out_idx,
+                             float* out_score, uint64_t* out_key, cudaStream_t s);
+
 struct BatchedLayout {
   __nv_bfloat16* qbf;
   float* qnorm;
@@ -34,7 +41,9 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   L.thr_ord = c.take<uint32_t>(L.clear_words);
   L.pool = L.thr_ord ? L.thr_ord + nq : nullptr;
   L.progress = L.thr_ord ? L.thr_ord + (size_t)nq * (1 + (size_t)k) : nullptr;
-  L.part = c.take<uint64_t>((size_t)2 * L.splits * nq * k);
+  size_t part_elems = (size_t)2 * L.splits * nq * k;
+  if (topk_few_supported(d, nq) && topk_few_part_elems(nq, k) > part_elems) part_elems = topk_few_part_elems(nq, k);
+  L.part = c.take<uint64_t>(part_elems);
   L.bytes = c.used();
   return L;
 }
@@ -72,6 +81,8 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
     HIPPO_CUDA(cudaMemsetAsync(L.part, 0, (size_t)nq * k * 8, s));
     return hippo_topk_merge(L.part, 1, nq, k, k, out_idx, out_score, out_key, stream);
   }
+  if (topk_few_supported(d, nq))   // two queries: one GEMV pass with two accumulators per row (topk_single.cu)
+    return topk_few_launch(bank, norm, n, q, nq, k, row_base, after_key, L.part, out_idx, out_score, out_key, s);
   HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, L.clear_words * 4, s));
   // queries -> bf16 + |a| (same pass the bank went through)
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);

@@ -7,6 +7,7 @@
 // that only rows passing a threshold test ever touch.  Per-block lists are merged by a
 // selection pass; a second tiny kernel merges the per-block results.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hippo {
 
@@ -178,6 +179,192 @@ topk_single_kernel(const __nv_bfloat16* __restrict__ bank, const float* __restri
       if (b == 0) prev = 0;
     }
   }
+}
+
+// ---- two queries per bank pass -------------------------------------------------------------------------------------
+// Between one query (the GEMV above) and the batches the tensor cores are built for lies the regime of a couple of
+// concurrent questions: through the tcgen05 kernel two queries cost 3.7 ms over a 10M-row bank (its 256-query tile is
+// mostly zero padding and is re-read for every bank tile), although the bank pass itself is the same 20.5 GB.  This
+// kernel is the GEMV with NQ accumulators per row: the rows are streamed ONCE, each 128-bit load is expanded to fp32
+// once and multiplied into NQ queries held in registers per 256-column chunk (the same FFMA order per query as the
+// single-query kernel, hence the same bits).  Lists, thresholds and the paging cursor are per query.
+// Measured on a 10M x 1024 bank (tools/batch_sweep.py): NQ = 2: 3.09 ms against 3.72 ms through tcgen05 (2.90 ms for
+// one query); NQ = 4: 4.47 ms against 4.19 ms, NQ = 8: 9.4 ms against 4.22 ms -- the register budget (218 - 240) leaves
+// one CTA of 8 warps per SM and the compiler sinks the prefetch loads into the arithmetic, so only NQ = 2 is
+// dispatched here; three and more queries stay on the tensor-core kernel.
+constexpr int kFewThreads = 256;
+constexpr int kFewWarps = kFewThreads / 32;
+
+template <int NQ>   // d == 1024 (four 256-column chunks); queries nq_real .. NQ-1 would be zero padding and produce nothing
+__global__ void __launch_bounds__(kFewThreads, 1)
+topk_few_kernel(const __nv_bfloat16* __restrict__ bank, const float* __restrict__ norm, int64_t n,
+                const float* __restrict__ q /*[nq_real][1024]*/, int nq_real, int k, int64_t row_base,
+                const uint64_t* __restrict__ after_key /*[nq_real] or null*/, uint64_t* __restrict__ part /*[grid][nq_real][k]*/) {
+  constexpr int d = 1024, CH = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);                                   // [NQ][1024], permuted as above
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NQ * d * 4);     // [NQ][warps][k]
+  __shared__ float s_an[NQ];
+  __shared__ double s_part[kFewWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  for (int qi = 0; qi < NQ; ++qi) {
+    double ss = 0.0;
+    for (int e = threadIdx.x; e < d; e += kFewThreads) {
+      const float v = qi < nq_real ? q[(size_t)qi * d + e] : 0.f;
+      ss += (double)v * (double)v;
+      const int c = e >> 8, l = (e >> 3) & 31, h = (e >> 2) & 1, j = e & 3;
+      sq[qi * d + (((c * 2 + h) * 32) + l) * 4 + j] = v;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) s_part[wid] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < kFewWarps; ++i) t += s_part[i];
+      s_an[qi] = __fsqrt_rn((float)t);        // |a| as the reference forms it: fp32 sqrt of the sum of squares
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NQ * kFewWarps * k; i += kFewThreads) lists[i] = 0;
+  __syncthreads();
+
+  float an[NQ], thr[NQ];
+  uint64_t below[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    an[qi] = s_an[qi];
+    thr[qi] = -INFINITY;
+    below[qi] = (after_key && qi < nq_real) ? after_key[qi] : ~0ull;
+  }
+
+  const int64_t ngroups = (n + kRowsPerIter - 1) / kRowsPerIter;
+  const int64_t gwarp = (int64_t)blockIdx.x * kFewWarps + wid;
+  const int64_t gstride = (int64_t)gridDim.x * kFewWarps;
+  // the loads of group g + 1 are issued before the arithmetic of group g (register double buffer): with NQ
+  // accumulators per row the kernel runs one CTA of 8 warps per SM, too few to hide the HBM latency by occupancy
+  // alone (measured without the prefetch: 5.4 ms for 4 queries over 10M rows against 2.9 ms for one)
+  auto load_group = [&](int64_t g, uint4 (&dst)[CH][kRowsPerIter]) {
+    const int64_t r0 = g * kRowsPerIter;
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) {
+      const int64_t row = r0 + r < n ? r0 + r : n - 1;
+      const __nv_bfloat16* rp = bank + row * (int64_t)d + lane * 8;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) dst[c][r] = ldg_stream(rp + c * 256);
+    }
+  };
+  uint4 w[CH][kRowsPerIter];
+  if (gwarp < ngroups) load_group(gwarp, w);
+  for (int64_t g = gwarp; g < ngroups; g += gstride) {
+    const int64_t r0 = g * kRowsPerIter;
+    uint4 wn[CH][kRowsPerIter];
+    load_group(g + gstride < ngroups ? g + gstride : g, wn);      // the last group is simply read again (L2 hit)
+    float acc[NQ][kRowsPerIter];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r) acc[qi][r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 qa[NQ], qb[NQ];
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        qa[qi] = *reinterpret_cast<const float4*>(&sq[qi * d + ((c * 2 + 0) * 32 + lane) * 4]);
+        qb[qi] = *reinterpret_cast<const float4*>(&sq[qi * d + ((c * 2 + 1) * 32 + lane) * 4]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r) {
+        const uint4 x = w[c][r];
+        const float x0 = bf16lo(x.x), x1 = bf16hi(x.x), x2 = bf16lo(x.y), x3 = bf16hi(x.y);
+        const float x4 = bf16lo(x.z), x5 = bf16hi(x.z), x6 = bf16lo(x.w), x7 = bf16hi(x.w);
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          float a = acc[qi][r];
+          a = fmaf(x0, qa[qi].x, a); a = fmaf(x1, qa[qi].y, a);
+          a = fmaf(x2, qa[qi].z, a); a = fmaf(x3, qa[qi].w, a);
+          a = fmaf(x4, qb[qi].x, a); a = fmaf(x5, qb[qi].y, a);
+          a = fmaf(x6, qb[qi].z, a); a = fmaf(x7, qb[qi].w, a);
+          acc[qi][r] = a;
+        }
+      }
+    }
+    const int64_t row = r0 + lane;                       // lane r owns row r0 + r
+    const bool mine = lane < kRowsPerIter && row < n;
+    const float bn = mine ? norm[row] : 1.f;
+    const float rbn = __frcp_rn(bn);
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+      if (qi < nq_real) {                                // warp-uniform
+#pragma unroll
+        for (int r = 0; r < kRowsPerIter; ++r) acc[qi][r] = warp_sum(acc[qi][r]);
+        float dot = acc[qi][0];
+#pragma unroll
+        for (int r = 1; r < kRowsPerIter; ++r) dot = lane == r ? acc[qi][r] : dot;
+        const bool cand = mine && !(dot * rbn < thr[qi]);
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+          uint64_t* mylist = lists + ((size_t)qi * kFewWarps + wid) * k;
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            if (lane == src) {
+              // the reference's operation order: dot / (|b| * |a|), IEEE fp32 (vo:182)
+              const float sc = __fdiv_rn(dot, __fmul_rn(bn, an[qi]));
+              const uint64_t key = pack_key(sc, (uint32_t)(row_base + row));
+              if (key < below[qi] && key > mylist[k - 1]) topk_insert(mylist, k, key);
+            }
+            __syncwarp();
+          }
+          thr[qi] = filter_threshold(mylist[k - 1], an[qi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r) w[c][r] = wn[c][r];
+  }
+  __syncthreads();
+  // block merge: warp (qi mod warps) selects the k best of query qi's kFewWarps * k candidates
+  for (int qi = wid; qi < nq_real; qi += kFewWarps) {
+    uint64_t prev = ~0ull;
+    for (int r = 0; r < k; ++r) {
+      const uint64_t b = prev ? warp_next_best(lists + (size_t)qi * kFewWarps * k, kFewWarps * k, prev, lane) : 0;
+      if (lane == 0) part[((size_t)blockIdx.x * nq_real + qi) * k + r] = b;
+      prev = b;
+    }
+  }
+}
+
+static int few_grid_for(const void* fn, size_t smem) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFewThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  return sm_count() * per_sm;
+}
+
+// Two queries of dimension 1024: one pass of the GEMV above + the per-query merge.  `part` needs
+// topk_few_part_elems(nq, k) 8-byte words.  HIPPO_FEW_QUERIES=0 sends these batches through the tensor-core kernel.
+bool topk_few_supported(int d, int nq) {
+  static const bool off = getenv("HIPPO_FEW_QUERIES") && atoi(getenv("HIPPO_FEW_QUERIES")) == 0;
+  return !off && d == 1024 && nq == 2;
+}
+size_t topk_few_part_elems(int nq, int k) { return (size_t)sm_count() * 2 * (size_t)nq * (size_t)k; }
+
+hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, const float* q, int nq, int k,
+                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int64_t* out_idx,
+                             float* out_score, uint64_t* out_key, cudaStream_t s) {
+  constexpr int NQ = 2;
+  HIPPO_REQUIRE(nq == NQ, "topk_few_launch: nq=%d", nq);
+  const size_t smem = (size_t)NQ * 1024 * 4 + (size_t)NQ * kFewWarps * k * 8;
+  const void* fn = (const void*)topk_few_kernel<NQ>;
+  int grid = few_grid_for(fn, smem);
+  const int64_t want = ((n + kRowsPerIter - 1) / kRowsPerIter + kFewWarps - 1) / kFewWarps;
+  if (want < grid) grid = (int)(want < 1 ? 1 : want);
+  topk_few_kernel<NQ><<<grid, kFewThreads, smem, s>>>((const __nv_bfloat16*)bank, norm, n, q, nq, k, row_base, after_key, part);
+  HIPPO_CUDA(cudaGetLastError());
+  return hippo_topk_merge(part, grid, nq, k, k, out_idx, out_score, out_key, (void*)s);
 }
 
 // keys [nparts, nq, k_in] -> best k per query; one warp per query.

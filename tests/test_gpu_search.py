@@ -112,6 +112,40 @@ def test_ragged_shapes_both_paths_agree_with_oracle(cuda_device, n, d, nq, k):
             assert np.all(idx[qi][kk:] == -1)
 
 
+@pytest.mark.parametrize("nq", [2, 3, 4, 5, 7, 8])
+def test_few_queries_ride_one_bank_pass(cuda_device, nq):
+    """A few queries of dimension 1024 behind the batched entry (two take the GEMV with two accumulators per row,
+    topk_single.cu; more go to the tensor cores): bit-equal to the single-query kernel on the lattice bank, within
+    the parity rule on Gaussian rows, NaN rows first, paging beyond HIPPO_TOPK_MAX, row counts off the 4-row groups."""
+    from hippomm_b200 import MemoryBank
+
+    bank_h, queries, fam = cases.search_lattice_small()
+    bank = MemoryBank.from_rows(bank_h)
+    bi, bs = _search(bank, queries[:nq], 10, "batched")
+    for qi in range(nq):
+        si, ss = _search(bank, queries[qi:qi + 1], 10, "single")
+        assert np.array_equal(bi[qi], si[0]) and np.array_equal(bs[qi].view(np.uint32), ss[0].view(np.uint32))
+    g = cases.golden()
+    for qi in range(nq):
+        check_topk_exact(bi[qi], bs[qi], g["search_lat_idx"][qi], g["search_lat_sim"][qi], what=f"few q{qi}")
+    rng = np.random.default_rng(100 + nq)
+    for n in (1, 3, 1021):
+        b = rng.standard_normal((n, 1024)).astype(np.float32)
+        if n > 2:
+            b[2] = 0.0                                        # zero-norm row: NaN, sorts first (vo:185)
+        q = rng.standard_normal((nq, 1024)).astype(np.float32)
+        bk = MemoryBank.from_rows(b)
+        k = 40 if n > 40 else 7                               # 40 pages through the per-query cursor
+        fi, fs = _search(bk, q, k, "batched")
+        for qi in range(nq):
+            si, ss = _search(bk, q[qi:qi + 1], k, "single")
+            check_topk(fi[qi][:min(k, n)], fs[qi][:min(k, n)], si[0][:min(k, n)], ss[0][:min(k, n)], what=f"few vs single n={n} q{qi}")
+            ri, rs = O.top_k_cosine_similarity(q[qi], b, k)
+            kk = min(k, n)
+            check_topk(fi[qi][:kk], fs[qi][:kk], ri, rs, what=f"few n={n} q{qi}")
+            assert np.all(fi[qi][kk:] == -1)
+
+
 def test_lattice_1m_planted_families(cuda_device):
     """1M-row lattice bank generated on the device: the top-10 of every query is its planted family
     (members 0..9, spread over the whole bank), identical from both kernels, scores bit-equal to the

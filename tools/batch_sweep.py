@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Search latency against batch size on the 10M x 1024 lattice bank (GEMV path for 1 query, tcgen05 path otherwise)."""
+"""Search latency against batch size on the 10M x 1024 lattice bank (GEMV for 1 query, the two-query GEMV behind
+the batched entry, tcgen05 beyond; HIPPO_FEW_QUERIES=0 sends the small batches through tcgen05 too; SWEEP=1,2,4 picks sizes)."""
 import json
 import os
 import sys
@@ -19,8 +20,8 @@ bench.build_bank(bank, rows, 0, rows, device)
 q_host, _ = synth.lattice_queries_np(bench.SEED, bench.NQ, bench.DIM, rows)
 q_dev = torch.from_numpy(q_host).to(device)
 out = []
-for nq, path in [(1, "single"), (1, "batched"), (8, "batched"), (64, "batched"), (256, "batched"), (512, "batched"),
-                 (1024, "batched"), (4096, "batched")]:
+sizes = [int(x) for x in os.environ.get("SWEEP", "1,2,3,4,8,16,64,256,512,1024,4096").split(",")]
+for nq, path in [(1, "single")] + [(x, "batched") for x in sizes]:
     q = q_dev[:nq].contiguous()
     for _ in range(3):
         bank.search_keys(q, 10, path)
