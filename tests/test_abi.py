@@ -62,3 +62,34 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
     assert "HMMA.16816" not in sass, "legacy mma.sync path present"
+
+
+def test_sass_of_the_streaming_kernels_uses_the_intended_instructions():
+    """The secondary kernels, by SASS: packed fp32 pairs and byte dot products in the SSIM kernel, a warp-level
+    REDUX + one 32-bit shared atomic (no 64-bit compare-and-swap loop) in the boundary kernel, 128-bit non-allocating
+    loads in the GEMV kernels."""
+    import pytest
+
+    def sass_of(pattern):
+        r = subprocess.run(["cuobjdump", "-sass", "-fun", pattern, str(_lib.LIB_PATH)], capture_output=True, text=True)
+        if r.returncode != 0 or "Function" not in r.stdout:
+            pytest.skip("cuobjdump unavailable or function not found")
+        return r.stdout
+
+    names = subprocess.run(["cuobjdump", "-elf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    import re
+
+    def mangled(fragment):
+        m = re.search(r"\.text\.(_Z\w*%s\w*)" % fragment, names)
+        if not m:
+            pytest.skip(f"{fragment} not found in the ELF listing")
+        return m.group(1)
+
+    ssim = sass_of(mangled("ssim_pair_kernel"))
+    for mnemonic in ("FFMA2", "FMUL2", "FADD2", "IDP.4A", "SHFL.DOWN", "MUFU.RCP"):
+        assert mnemonic in ssim, f"{mnemonic} missing from ssim_pair_kernel"
+    seg = sass_of(mangled("segment_kernel"))
+    assert "REDUX" in seg and "ATOMS.MAX" in seg, "boundary kernel: warp reduce + native shared atomic expected"
+    assert "ATOMS.CAST.SPIN.64" not in seg, "boundary kernel: 64-bit compare-and-swap loop is back"
+    few = sass_of(mangled("topk_few_kernel"))
+    assert "LDG.E.NA.128" in few or "LDG.E.128" in few, "two-query GEMV: 128-bit loads expected"
