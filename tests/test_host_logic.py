@@ -191,3 +191,32 @@ def test_block_sum_classifier_never_contradicts_the_exact_level():
     assert _window_class_model(e512, ns, ns, ns, 8000, -40.0) == 1 and O.compute_audio_level(x[ns:ns]) == -100
     assert _window_class_model(e512, 0, 8000, ns, 8000, -100.0) == 2      # all-zero windows need the exact rule there
     assert decided > 1000 and undecided > 50
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/ (own arm and reference arm) carry every key of the bench contract."""
+    import glob
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    own = sorted(glob.glob(os.path.join(root, "profiles", "r1_v*_bench.json")))[-1]
+    line = json.loads(open(own).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline"):
+        assert key in line, key
+    assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert line["roofline"]["bound"] in ("hbm", "tensor")
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ref = json.loads(open(own.replace("_bench.json", "_bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
+    assert ref["cpu_baseline"]["value"] == ref["value"] == ref["e2e"]["value"]
