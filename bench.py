@@ -214,6 +214,29 @@ def build_bank(bank, n_local, row0, n_total, device):
     torch.cuda.synchronize()
 
 
+def parity_gate(idx, score, q_host, expect, n_total, k, first, count):
+    """True iff every query's rows are its planted family and, for queries [first, first + count), rows, order and
+    score BITS equal the oracle's (the restated vo:151-188 run on the candidate rows of those queries plus a
+    2,000-row slab of unrelated rows)."""
+    from hippomm_b200 import synth
+    from oracle import hippo_oracle as O
+
+    got = idx.cpu().numpy()
+    sc = score.cpu().numpy()
+    if not np.array_equal(np.sort(got, axis=1), expect):
+        log("[gate] rows differ from the planted families")
+        return False
+    sel = np.arange(first, first + count) % len(q_host)
+    rows = np.unique(np.concatenate([expect[sel].reshape(-1), np.arange(n_total - 2000, n_total)]))
+    sub = synth.lattice_rows_np(SEED, rows, DIM, n_total)
+    for qi in sel:
+        ri, rs = O.top_k_cosine_similarity(q_host[qi], sub, k)
+        if not (np.array_equal(rows[ri], got[qi]) and np.array_equal(rs.view(np.uint32), sc[qi].view(np.uint32))):
+            log(f"[gate] query {qi}: rows / score bits differ from the oracle")
+            return False
+    return True
+
+
 def timed_steps(fn, steps, warmup, barrier):
     import torch
 
@@ -325,43 +348,44 @@ def run_gpu_arm(args):
     out_idx_host = torch.empty((NQ, k), dtype=torch.int64).pin_memory()
     out_score_host = torch.empty((NQ, k), dtype=torch.float32).pin_memory()
 
+    staged = []
+
     def step_e2e():
-        """Public API with host buffers: H2D of the queries, search, D2H of (rows, scores)."""
+        """Public API with host buffers: H2D of the queries, search, D2H of (rows, scores), host sync every step.
+        The upload of the NEXT step's queries is started (MemoryBank.stage_queries, copy stream) before this step's
+        search is issued, so the DMA runs under the tensor-core pass; every step still uploads its own 16 MB."""
+        cur = staged.pop() if staged else bank.stage_queries(q_pinned)
+        staged.append(bank.stage_queries(q_pinned))
         if world > 1:
-            qd = q_pinned.to(device, non_blocking=True)
-            _, _, kk = bank.search_keys(qd, k, "batched")
+            _, _, kk = bank.search_keys(cur, k, "batched")
             i2, s2, _ = exchange_merge(kk)
         else:
-            i2, s2 = bank.search(q_pinned, k, "batched")
+            i2, s2 = bank.search(cur, k, "batched")
         out_idx_host.copy_(i2, non_blocking=True)
         out_score_host.copy_(s2, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    # correctness gate before timing: planted families + bit-exact scores on a sample (oracle = checker)
+    # correctness gate before timing, on EVERY rank: planted families for all 4,096 queries + bit-exact scores and
+    # rows against the oracle (vo:151-188 restated) for 32 queries of this rank's own slice (oracle = checker)
     i0, s0, _ = step_device()
     torch.cuda.synchronize()
     expect = synth.lattice_expected_topk(fam, n_total, k)
-    got = np.sort(i0.cpu().numpy(), axis=1)
-    if not np.array_equal(got, expect) and not os.environ.get("HIPPO_TC_DEBUG"):
-        raise SystemExit("bench: search result differs from the planted families -- refusing to time a wrong kernel")
-    if rank == 0:
-        from oracle import hippo_oracle as O
-
-        rows = np.unique(expect[:2].reshape(-1))
-        sub = synth.lattice_rows_np(SEED, rows, DIM, n_total)
-        for qi in range(2):
-            ri, rs = O.top_k_cosine_similarity(q_host[qi], sub, k)
-            if os.environ.get("HIPPO_TC_DEBUG"):
-                break
-            if not (np.array_equal(rows[ri], i0[qi].cpu().numpy())
-                    and np.array_equal(rs.view(np.uint32), s0[qi].cpu().numpy().view(np.uint32))):
-                raise SystemExit("bench: scores are not bit-equal to the oracle on the lattice bank")
-    log(f"[rank {rank}] parity gate ok (planted top-{k} families, bit-exact scores)")
+    gate_ok = parity_gate(i0, s0, q_host, expect, n_total, k, first=(32 * rank) % NQ, count=32)
+    if dist is not None:
+        flag = torch.tensor([1 if gate_ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gate_ok = bool(flag.item())
+    if not gate_ok and not os.environ.get("HIPPO_TC_DEBUG"):
+        raise SystemExit("bench: search result differs from the oracle -- refusing to time a wrong kernel")
+    log(f"[rank {rank}] parity gate ok (planted top-{k} families for {NQ} queries, rows + bit-exact scores vs the oracle "
+        f"for queries [{(32 * rank) % NQ}, {(32 * rank) % NQ + 32}))")
 
     with ClockSampler(local_rank) as clk:
         elapsed = max_over_ranks(timed_steps(step_device, args.steps, args.warmup, barrier))
     clocks = clk.summary()
     e2e_elapsed = max_over_ranks(timed_steps(step_e2e, args.steps, args.warmup, barrier))
+    if not np.array_equal(np.sort(out_idx_host.numpy(), axis=1), expect) and not os.environ.get("HIPPO_TC_DEBUG"):
+        raise SystemExit("bench: the end-to-end step returned rows that differ from the planted families")
 
     qps = NQ * args.steps / elapsed
     e2e_qps = NQ * args.steps / e2e_elapsed
@@ -396,7 +420,8 @@ def run_gpu_arm(args):
         "roofline": roof,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(q_pinned.numel() * 4),
                 "d2h_bytes_per_step": int(NQ * k * 12), "ms_per_step": e2e_elapsed / args.steps * 1e3,
-                "note": "queries from pinned host memory, results to host; bank resident (built once)"},
+                "note": "queries from pinned host memory (upload of step i + 1 overlapped with the search of step i), results "
+                        "to pinned host memory and a host synchronisation every step; bank resident (built once)"},
         "gpu_launches": 3 * args.steps + (args.steps if world > 1 else 0),
         "clocks": clocks,
     }
@@ -414,34 +439,127 @@ def run_gpu_arm(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if world > 1 and not args.no_extra:
-        # config 5: single-query latency over the sharded bank, one query in flight -- GEMV over this rank's shard,
-        # then the exchange + merge; every rank issues the same calls, rank 0 reports its own clock
-        lat = []
-        for i in range(3 + 200):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _, _, kk = bank.search_keys(q_dev[i % NQ].reshape(1, DIM), k, "single")
-            exchange_merge(kk)
-            e1.record()
-            e1.synchronize()
-            if i >= 3:
-                lat.append(e0.elapsed_time(e1))
-        lat.sort()
-        bytes_ = n_local * DIM * 2 + n_local * 4
+        extra5 = run_sharded_extras(bank, q_dev, exchange_merge, exchange, peaks, device, rank, world, dist, args,
+                                    barrier, max_over_ranks, n_total, n_local)
         if rank == 0:
-            line["extra"] = {"sharded_single_query": {
-                "latency_ms": {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99) - 1], "min": lat[0],
-                               "max": lat[-1], "samples": len(lat)},
-                "queries_per_s": 1e3 / lat[len(lat) // 2],
-                "roofline": {"bound": "hbm", "achieved": bytes_ / (lat[len(lat) // 2] * 1e-3) / 1e9, "peak": peaks["hbm"],
-                             "unit": "GB/s per GPU", "frac": bytes_ / (lat[len(lat) // 2] * 1e-3) / 1e9 / peaks["hbm"]},
-                "config": f"1 query top-{k} over {n_total} rows sharded over {world} GPUs ({n_local} rows per GPU), "
-                          f"exchange {exchange}"}}
+            line["extra"] = extra5
     barrier()
     if rank == 0:
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def latency_stats(lat):
+    lat = sorted(lat)
+    return {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99) - 1], "min": lat[0], "max": lat[-1],
+            "samples": len(lat)}
+
+
+def run_sharded_extras(bank, q_dev, exchange_merge, exchange, peaks, device, rank, world, dist, args, barrier,
+                       max_over_ranks, n_total, n_local):
+    """N > 1 only.  (a) single-query latency over the strong-scaling shards of the metric's 10M-row bank;
+    (b) BASELINE.json config 5: a bank of 10M rows PER GPU (80M rows at 8 GPUs), weak scaling -- batched throughput,
+    single-query p50 / p99 over 1,000 queries with one in flight, and its own parity gate."""
+    import torch
+
+    from hippomm_b200 import MemoryBank, _cuda, _lib, synth
+    from hippomm_b200.distributed import shard_range
+
+    lib = _lib.load()
+    k = TOPK
+    out = {}
+
+    def single_latency(bk, queries, nrep):
+        lat = []
+        for i in range(3 + nrep):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, _, kk = bk.search_keys(queries[i % NQ].reshape(1, DIM), k, "single")
+            exchange_merge(kk)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                lat.append(e0.elapsed_time(e1))
+        # every rank timed its own clock; the slowest rank's percentile is the job's
+        st = latency_stats(lat)
+        for key in ("p50", "p99", "min", "max"):
+            st[key] = max_over_ranks(st[key])
+        return st
+
+    def hbm_roof(rows_local, ms):
+        bytes_ = rows_local * DIM * 2 + rows_local * 4
+        gbs = bytes_ / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s per GPU", "frac": gbs / peaks["hbm"],
+                "algorithmic_bytes_per_gpu": bytes_}
+
+    st = single_latency(bank, q_dev, 200)
+    out["sharded_single_query"] = {
+        "latency_ms": st, "queries_per_s": 1e3 / st["p50"], "roofline": hbm_roof(n_local, st["p50"]),
+        "config": f"1 query top-{k} over {n_total} rows sharded over {world} GPUs ({n_local} rows per GPU), exchange {exchange}"}
+
+    # ---- config 5 ----
+    rows_per_gpu = args.config5_rows_per_gpu
+    n5 = rows_per_gpu * world
+    lo5, hi5 = shard_range(n5, rank, world)
+    t0 = time.perf_counter()
+    bank5 = MemoryBank(hi5 - lo5, DIM, device=device, row_base=lo5)
+    build_bank(bank5, hi5 - lo5, lo5, n5, device)
+    q5_host, fam5 = synth.lattice_queries_np(SEED, NQ, DIM, n5)
+    q5 = torch.from_numpy(q5_host).to(device)
+    log(f"[rank {rank}] config 5: bank rows [{lo5}, {hi5}) of {n5} built in {time.perf_counter() - t0:.1f}s")
+
+    def step5():
+        _, _, kk = bank5.search_keys(q5, k, "batched")
+        return exchange_merge(kk)
+
+    # parity gate 1: planted families for all 4,096 queries, rows + score bits against the oracle for 8 queries on
+    # EVERY rank (different queries per rank)
+    i5, s5, _ = step5()
+    torch.cuda.synchronize()
+    expect5 = synth.lattice_expected_topk(fam5, n5, k)
+    ok = parity_gate(i5, s5, q5_host, expect5, n5, k, first=(8 * rank) % NQ, count=8)
+    # parity gate 2: the G-GPU answer over the bank's first `rows_per_gpu` rows (sharded over all ranks) must equal
+    # the 1-GPU answer over the same rows -- rank 0's own shard IS that prefix -- bit for bit
+    plo, phi = shard_range(rows_per_gpu, rank, world)
+    prefix = MemoryBank(phi - plo, DIM, device=device, row_base=plo)
+    build_bank(prefix, phi - plo, plo, n5, device)
+    _, _, kp = prefix.search_keys(q5[:512].contiguous(), k, "batched")
+    gi, gs, _ = exchange_merge(kp)
+    if rank == 0:
+        oi, os_ = bank5.search(q5[:512].contiguous(), k, "batched")
+        same = bool(torch.equal(oi, gi)) and bool(torch.equal(os_.view(torch.int32), gs.view(torch.int32)))
+        if not same:
+            log("[gate] config 5: sharded answer over the 10M-row prefix differs from the single-GPU answer")
+        ok = ok and same
+    del prefix
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        raise SystemExit("bench: config 5 parity gate failed")
+    log(f"[rank {rank}] config 5 parity gate ok")
+
+    elapsed = max_over_ranks(timed_steps(step5, args.steps, args.warmup, barrier))
+    ms = elapsed / args.steps * 1e3
+    tf = 2.0 * NQ * (hi5 - lo5) * DIM / (elapsed / args.steps) / 1e12
+    st5 = single_latency(bank5, q5, 1000)
+    out["config5_weak"] = {
+        "bank_rows": n5, "rows_per_gpu": hi5 - lo5, "queries_per_step": NQ, "k": k, "exchange": exchange,
+        "queries_per_s": NQ * args.steps / elapsed, "ms_per_step": ms, "scaling": "weak",
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s per GPU",
+                     "frac": tf / peaks["tf_sustained"], "frac_of_burst": tf / peaks["tf_burst"]},
+        "single_query": {"latency_ms": st5, "queries_per_s": 1e3 / st5["p50"], "roofline": hbm_roof(hi5 - lo5, st5["p50"]),
+                         "note": "1,000 queries, one in flight: GEMV over the local shard + fused exchange / merge; "
+                                 "max over ranks of each rank's percentile"},
+        "parity_gate": "planted families for 4,096 queries on every rank; rows + score bits vs the oracle (restated "
+                       "vo:151-188 on the candidate rows + a 2,000-row slab) for 8 queries per rank; sharded answer over "
+                       "the first 10M rows == single-GPU answer over the same rows, bit for bit (512 queries)",
+        "config": f"BASELINE config 5: {NQ} queries top-{k} over a {n5}x{DIM} bank, {hi5 - lo5} rows per GPU on {world} GPUs",
+    }
+    log(f"[rank {rank}] config 5: {ms:.2f} ms/step, {NQ * args.steps / elapsed:.0f} q/s, single-query p50 {st5['p50']:.3f} ms")
+    del bank5
+    torch.cuda.empty_cache()
+    return out
 
 
 # ncu `--set full` capture of sim_tc_kernel<EPI_TOPK> (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
@@ -460,37 +578,10 @@ TRAFFIC = _load_traffic()
 
 
 def synth_stream_hour(device, nf=3600, h=224, w=224, sr=16000):
-    """Config 2's synthetic stream, generated on the device: piecewise-static scenes of 5-60 s (smooth field +
-    per-frame noise of 2 grey levels), int16 noise at -20 dBFS with silences of 0.6-3 s every 8-40 s."""
-    import torch
+    """Config 2's synthetic stream (hippomm_b200.synth.stream_hour_torch, seed 1), generated on the device."""
+    from hippomm_b200 import synth
 
-    g = torch.Generator(device=device)
-    g.manual_seed(1)
-    frames = torch.empty((nf, h, w, 3), dtype=torch.uint8, device=device)
-    f0 = 0
-    while f0 < nf:
-        length = int(torch.randint(5, 61, (1,), generator=g, device=device).item())
-        m = min(length, nf - f0)
-        yy = torch.linspace(0, 6.28, h, device=device)[:, None, None]
-        xx = torch.linspace(0, 6.28, w, device=device)[None, :, None]
-        ph = torch.rand((1, 1, 3), generator=g, device=device) * 6.28
-        fr = torch.rand((2,), generator=g, device=device) * 3 + 0.5
-        field = 128 + 40 * torch.sin(fr[0] * xx + ph) + 40 * torch.cos(fr[1] * yy + ph)
-        noisy = field[None] + 2.0 * torch.randn((m, h, w, 3), generator=g, device=device)
-        frames[f0:f0 + m] = noisy.round().clamp(0, 255).to(torch.uint8)
-        f0 += m
-    ns = nf * sr
-    pcm = (torch.randn((ns, 1), generator=g, device=device) * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
-    t_s = 0
-    while True:
-        t_s += int(torch.randint(8, 41, (1,), generator=g, device=device).item())
-        if t_s >= nf - 3:
-            break
-        ln = int((0.6 + 2.4 * torch.rand((1,), generator=g, device=device).item()) * sr)
-        pcm[t_s * sr:t_s * sr + ln] = (pcm[t_s * sr:t_s * sr + ln].float() * 1e-3).round().to(torch.int16)
-        t_s += 3
-    ft = torch.arange(nf, dtype=torch.float64, device=device)
-    return frames, pcm, ft
+    return synth.stream_hour_torch(device, nf, h, w, sr, seed=1)
 
 
 def run_extras(bank, q_dev, peaks, device, lib):
@@ -779,6 +870,8 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--bank-rows", type=int, default=BANK_ROWS, help="total bank rows (default: the 10M of the metric)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary kernels and the CPU baseline")
+    ap.add_argument("--config5-rows-per-gpu", type=int, default=BANK_ROWS,
+                    help="rows per GPU of the weak-scaling bank of config 5 (N > 1 only; 10M = 80M rows at 8 GPUs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -12,13 +12,13 @@ There is no CPU fallback: without the library or without an sm_100 GPU the calls
 from __future__ import annotations
 
 from . import _lib
-from .bank import MemoryBank
-from .consolidation import select_key_frames, select_key_frames_device
+from .bank import MemoryBank, search_rows
+from .consolidation import RecheckOverflow, checked_key_frames, select_key_frames, select_key_frames_device
 from .events import EventBank, find_relevant_segments
 from .prefilter import dedup_window_frames, select_saved_frames
 from .segmentation import (SequenceSegment, compute_audio_level, compute_frame_difference,
                            compute_frame_similarity, segment_sequence)
-from .vector_ops import cosine_similarity, set_bank_cache, top_k_cosine_similarity
+from .vector_ops import cosine_similarity, invalidate_bank_cache, set_bank_cache, top_k_cosine_similarity
 
 __version__ = "0.1.0"
 
@@ -26,6 +26,7 @@ __all__ = [
     "MemoryBank", "SequenceSegment", "top_k_cosine_similarity", "cosine_similarity", "select_key_frames",
     "select_key_frames_device", "segment_sequence", "compute_frame_similarity", "compute_audio_level",
     "compute_frame_difference", "EventBank", "find_relevant_segments", "select_saved_frames", "dedup_window_frames",
+    "search_rows", "checked_key_frames", "RecheckOverflow", "set_bank_cache", "invalidate_bank_cache",
     "install", "uninstall", "library_path",
 ]
 
@@ -72,7 +73,8 @@ def install(cache_banks: bool = False) -> None:
 
     `hippomm` must be importable.  Modules that cannot be imported (missing third-party packages) are
     skipped; at least vector_ops must succeed.  cache_banks=True keeps device banks of recently searched
-    feature arrays (keyed by array identity + fingerprint) so repeated queries skip the upload.
+    feature arrays that are READ-ONLY (`arr.flags.writeable = False`; keyed by object identity) so repeated
+    queries skip the upload; writeable arrays are searched straight from the upload on every call.
     """
     import importlib
 

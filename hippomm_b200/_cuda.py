@@ -66,6 +66,12 @@ def to_device(a, device: torch.device, dtype: torch.dtype | None = None) -> torc
             t = t.to(dtype)
         return t.to(device, non_blocking=True).contiguous()
     arr = np.ascontiguousarray(a)
+    if not arr.flags.writeable:          # read-only arrays are only ever read here; torch just cannot express that
+        arr = arr.view()
+        try:
+            arr.flags.writeable = True
+        except ValueError:               # a buffer that really is read-only (bytes, mmap): copy
+            arr = np.array(arr)
     t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)

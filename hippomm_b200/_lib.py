@@ -19,7 +19,7 @@ HIPPO_E_WORKSPACE = -5
 
 HIPPO_F32, HIPPO_F64, HIPPO_BF16, HIPPO_I16 = 0, 1, 2, 3
 HIPPO_TOPK_MAX = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HippoError(RuntimeError):
@@ -75,6 +75,9 @@ SIGNATURES = {
     "hippo_topk_single": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "hippo_topk_batched_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I32]),
     "hippo_topk_batched": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "hippo_topk_rows_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "hippo_topk_rows": (_I32, [_P, _I32, _I64, _I32, _I64, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "hippo_rescore": (_I32, [_P, _I32, _I64, _I32, _I64, _I64, _P, _I32, _I32, _P, _I32, _P, _P, _P]),
     "hippo_topk_merge": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hippo_topk_exchange_bytes": (_SZ, [_I32, _I32, _I32]),
     "hippo_topk_exchange_merge": (_I32, [_P, _I32, _I32, _I32, _P, _SZ, _I32, _I32, C.c_uint32, _P, _P, _P, _P]),
@@ -84,6 +87,8 @@ SIGNATURES = {
     "hippo_recall_windows": (_I32, [_P, _P, _I32, _I32, _P, _P, _P, _F64, _I32, _P, _P, _P, _P, _P, _P]),
     "hippo_consolidate_workspace_bytes": (_SZ, [_I64, _I32]),
     "hippo_consolidate": (_I32, [_P, _I64, _I32, _F32, _F32, _F32, _P, _P, _P, _P, _SZ, _P]),
+    "hippo_consolidate_ex_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I64]),
+    "hippo_consolidate_ex": (_I32, [_P, _I64, _I32, _F32, _F32, _F32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "hippo_frame_pairs_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "hippo_frame_pairs": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _SZ, _P]),
     "hippo_audio_energy": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P]),

@@ -26,6 +26,7 @@ SOURCES = [
     "bank_build.cu",
     "topk_single.cu",
     "topk_batched.cu",
+    "topk_rows.cu",
     "recall.cu",
     "exchange.cu",
     "sim_tc.cu",

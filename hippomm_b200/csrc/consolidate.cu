@@ -376,9 +376,9 @@ __global__ void iota_kernel(int64_t n, int64_t* out_keep, int32_t* out_count) {
   if (threadIdx.x == 0) *out_count = (int32_t)n;
 }
 
-static int cons_band() {
+static int cons_band(int requested = 0) {
   const char* e = getenv("HIPPO_CONS_BAND");
-  int b = e ? atoi(e) : kConsBandDefault;
+  int b = requested > 0 ? requested : (e ? atoi(e) : kConsBandDefault);
   if (b < kScanRows) b = kScanRows;
   if (b > (kAdvMaxWords - 32) * 32) b = (kAdvMaxWords - 32) * 32;
   return b / kScanRows * kScanRows;
@@ -399,7 +399,12 @@ struct ConsLayout {
   size_t bytes;
 };
 
-static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int band) {
+// default capacity of the near-threshold pair list (drained after every band)
+static int64_t cons_default_cap(int64_t n, int band) {
+  return 64 * ((n < (int64_t)band ? n : (int64_t)band) + 1024) + (1 << 20);
+}
+
+static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int band, int64_t unc_cap = 0) {
   Carver c(ws, ws_bytes);
   ConsLayout L{};
   L.X = c.take<__nv_bfloat16>((size_t)n * d);
@@ -414,7 +419,8 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int b
   L.kept[0] = c.take<unsigned long long>((size_t)L.kept_words);
   L.kept[1] = c.take<unsigned long long>((size_t)L.kept_words);
   // the list is drained after every band
-  int64_t cap = 64 * ((n < (int64_t)band ? n : (int64_t)band) + 1024) + (1 << 20);
+  int64_t cap = unc_cap > 0 ? unc_cap : cons_default_cap(n, band);
+  if (cap > 0x7fffff00ll) cap = 0x7fffff00ll;
   L.unc_cap = (int32_t)cap;
   L.unc = c.take<uint2>((size_t)cap);
   L.counters = c.take<int32_t>(64);
@@ -427,13 +433,24 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int b
 extern "C" {
 
 size_t hippo_consolidate_workspace_bytes(int64_t n, int32_t d) {
-  if (n <= 2 || d <= 0) return 256;
-  return hippo::cons_layout(nullptr, 0, n, d, hippo::cons_band()).bytes;
+  return hippo_consolidate_ex_workspace_bytes(n, d, 0, 0);
 }
 
 hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float gamma, float band_exact,
                                float band_inexact, int64_t* out_keep, int32_t* out_count,
                                int32_t* out_stats, void* ws, size_t ws_bytes, void* stream) {
+  return hippo_consolidate_ex(feats, n, d, gamma, band_exact, band_inexact, 0, 0, out_keep, out_count, out_stats, ws,
+                              ws_bytes, stream);
+}
+
+size_t hippo_consolidate_ex_workspace_bytes(int64_t n, int32_t d, int32_t band_rows, int64_t uncertain_cap) {
+  if (n <= 2 || d <= 0) return 256;
+  return hippo::cons_layout(nullptr, 0, n, d, hippo::cons_band(band_rows), uncertain_cap).bytes;
+}
+
+hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, float gamma, float band_exact,
+                                  float band_inexact, int32_t band_rows, int64_t uncertain_cap, int64_t* out_keep,
+                                  int32_t* out_count, int32_t* out_stats, void* ws, size_t ws_bytes, void* stream) {
   using namespace hippo;
   HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "hippo_consolidate: need d %% 64 == 0 (d=%d)", d);
   HIPPO_REQUIRE(n < 0x7fffffffll, "hippo_consolidate: n too large");
@@ -447,8 +464,9 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
     HIPPO_CUDA(cudaGetLastError());
     return HIPPO_OK;
   }
-  const int band = cons_band();
-  ConsLayout L = cons_layout(ws, ws_bytes, n, d, band);
+  HIPPO_REQUIRE(band_rows >= 0 && uncertain_cap >= 0, "hippo_consolidate: negative band_rows / uncertain_cap");
+  const int band = cons_band(band_rows);
+  ConsLayout L = cons_layout(ws, ws_bytes, n, d, band, uncertain_cap);
   if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
     set_error("hippo_consolidate: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;

@@ -83,7 +83,9 @@ class PeerExchange:
         idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         score = torch.empty((nq, k), dtype=torch.float32, device=dev)
         key = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        self.epoch = self.epoch % 0xFFFFFFFF + 1      # 1 .. 2^32 - 1, never 0 (the cleared state of the flags)
+        # 1, 2, ..., 2^32 - 1, then 2, 3, ...: never 0 (the cleared state of the flags), and the parity -- which of
+        # the two gather buffers a call uses -- keeps alternating across the wrap (2^32 - 1 is odd, 2 is even)
+        self.epoch = self.epoch + 1 if self.epoch < 0xFFFFFFFF else 2
         with torch.cuda.device(dev):
             _lib.check(lib.hippo_topk_exchange_merge(
                 keys.contiguous().data_ptr(), nq, k_in, k, self.handle.buffer_ptrs_dev, self.nbytes, self.rank,
@@ -117,14 +119,23 @@ class ShardedBank:
         if self.exchange == "nccl" or self.world == 1 or self._peer_failed:
             return None
         if self._peer is None or not self._peer.fits(nq, k):
+            # collective: every rank reaches this with the same (nq, k).  The outcome is agreed on by ALL ranks: a rank
+            # that fell back to NCCL on its own would leave the others spinning on flags that never arrive.
+            err = None
             try:
-                # collective: every rank reaches this with the same (nq, k)
-                self._peer = PeerExchange(max(nq, 4096), max(k, _lib.HIPPO_TOPK_MAX), self.local.device, self.group)
+                peer = PeerExchange(max(nq, 4096), max(k, _lib.HIPPO_TOPK_MAX), self.local.device, self.group)
             except Exception as e:  # no peer access / symmetric memory unavailable
+                peer, err = None, f"{type(e).__name__}: {e}"
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=self.local.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._peer = None
+                self._peer_failed = err or "peer exchange unavailable on another rank"
                 if self.exchange == "p2p":
-                    raise
-                self._peer_failed = f"{type(e).__name__}: {e}"
+                    raise RuntimeError(f"exchange='p2p' requested but the peer exchange could not be set up on every "
+                                       f"rank ({self._peer_failed})")
                 return None
+            self._peer = peer
         return self._peer
 
     def fill_local(self, start_local: int, rows) -> None:

@@ -130,16 +130,20 @@ def compute_frame_difference(frame1: np.ndarray, frame2: np.ndarray) -> float:
 
 
 # ------------------------------------------------------------------- audio ----
-def _audio_to_device(audio_data, dev):
-    """Host audio (n,) / (n, ch) of int16 / float32 / float64 -> device tensor in its own dtype."""
+def _audio_to_device(audio_data, dev, int16_pcm: bool = False):
+    """Host audio (n,) / (n, ch) -> device tensor.  float32 / float64 pass through; every other dtype is converted
+    to float64 WITHOUT scaling, which is what the reference's arithmetic does with it (`mean(axis=1)` / `np.mean`
+    promote integers to float64, hm:995-998; the int16 wrap-around of `np.square` on a 1-D integer array is not
+    reproduced).  int16_pcm=True keeps int16 samples as PCM (x = k / 32768, what `sf.read` hands the reference for
+    pcm_s16le, bp:331-335): half the upload, exact sums."""
     if isinstance(audio_data, torch.Tensor):
         t = audio_data.detach()
-        if t.dtype not in _PCM_ENUM:
+        if not (t.dtype in (torch.float32, torch.float64) or (int16_pcm and t.dtype == torch.int16)):
             t = t.to(torch.float64)
         t = t.to(dev, non_blocking=True)
     else:
         a = np.asarray(audio_data)
-        if a.dtype not in (np.int16, np.float32, np.float64):
+        if not (a.dtype in (np.float32, np.float64) or (int16_pcm and a.dtype == np.int16)):
             a = a.astype(np.float64)
         t = _cuda.to_device(a, dev)
     if t.dim() == 1:
@@ -178,10 +182,11 @@ def audio_levels_device(pcm: torch.Tensor, win_start: torch.Tensor, win_len: tor
     return out[: ws_.numel()]
 
 
-def compute_audio_level(audio_data, sample_rate=None) -> float:
-    """RMS level of an audio segment in dB, -100 for digital silence (hm:993-1000). `sample_rate` is unused."""
+def compute_audio_level(audio_data, sample_rate=None, *, int16_pcm: bool = False) -> float:
+    """RMS level of an audio segment in dB, -100 for digital silence (hm:993-1000). `sample_rate` is unused.
+    Integer input is taken at face value like the reference does; int16_pcm=True reads int16 as k / 32768."""
     dev = _cuda.require_device()
-    pcm = _audio_to_device(audio_data, dev)
+    pcm = _audio_to_device(audio_data, dev, int16_pcm)
     n = pcm.shape[0]
     lv = audio_levels_device(pcm, torch.tensor([0], dtype=torch.int64), torch.tensor([n], dtype=torch.int64))
     return float(lv.item())
@@ -298,10 +303,11 @@ def segment_boundaries_device(ssim: Optional[torch.Tensor], frame_times: Optiona
 def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio_sample_rate=None, *,
                      max_segment_duration: float = 30.0, min_segment_duration: float = 10.0,
                      frame_similarity_threshold: float = 0.95, audio_silence_threshold: float = -40,
-                     ) -> List[SequenceSegment]:
+                     int16_pcm: bool = False) -> List[SequenceSegment]:
     """Drop-in for HippocampalMemory._segment_sequence (hm:1002-1114); thresholds default to
     config/default_config.yaml:27-30.  `video_frames` may be paths (as in the reference), BGR arrays,
-    or one uint8 array [n, h, w, 3]."""
+    or one uint8 array [n, h, w, 3].  Integer audio is taken at face value, as the reference's NumPy
+    arithmetic does; int16_pcm=True reads int16 samples as PCM (k / 32768, what sf.read yields, bp:331-335)."""
     segments: List[SequenceSegment] = []
     if video_frames is None and audio_data is None:                                   # hm:1024-1025
         return segments
@@ -340,7 +346,7 @@ def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio
     if has_audio:
         if int(0.5 * audio_sample_rate) < 1:
             raise ValueError("range() arg 3 must not be zero")                      # hm:1068 with a tiny rate
-        pcm_d = _audio_to_device(audio_data, dev)
+        pcm_d = _audio_to_device(audio_data, dev, int16_pcm)
         pyr = audio_energy_device(pcm_d)
 
     max_segments = int(math.ceil(total / min_segment_duration)) + 2

@@ -219,3 +219,67 @@ def audio_stream_int16(seed: int, n_samples: int, sample_rate: int = 16000, leve
         out[a:b] = np.clip(np.rint(rng.normal(0.0, samp, size=b - a)), -32768, 32767).astype(np.int16)
         t += length
     return out
+
+
+# ------------------------------------------------- device-side generators (torch) ----
+# Used where the data set is too large to be born on the host (bench.py, the full-size GPU tests); the oracle
+# side simply downloads the tensor, so both sides see the same bytes.
+def videolike_features_torch(seed: int, n_scenes: int, frames_per_scene: int, device, d: int = 1024,
+                             step: float = 0.12, scene_batch: int = 200):
+    """fp32 [n_scenes * frames_per_scene, d] time-ordered video-like rows (scene centre ~ N(0, I), random walk of
+    `step` per frame) generated on `device`; the same construction as videolike_features, different stream."""
+    feats = torch.empty((n_scenes * frames_per_scene, d), dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    fps = frames_per_scene
+    for s0 in range(0, n_scenes, scene_batch):
+        m = min(scene_batch, n_scenes - s0)
+        v = torch.randn((m, d), generator=g, device=device)
+        for f in range(fps):
+            feats[(s0 * fps + f)::fps][:m] = v
+            v = v + step * torch.randn((m, d), generator=g, device=device)
+    return feats
+
+
+def gaussian_rows_torch(seed: int, n: int, d: int, device, chunk: int = 1 << 18):
+    """fp32 [n, d] i.i.d. N(0, 1) rows generated on `device` (SURVEY §8d config 4's second bank, seed 5)."""
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    for r0 in range(0, n, chunk):
+        m = min(chunk, n - r0)
+        out[r0:r0 + m] = torch.randn((m, d), generator=g, device=device)
+    return out
+
+
+def stream_hour_torch(device, nf: int = 3600, h: int = 224, w: int = 224, sr: int = 16000, seed: int = 1):
+    """Config 2's synthetic stream, generated on the device: piecewise-static scenes of 5-60 s (smooth field +
+    per-frame noise of 2 grey levels), int16 noise at -20 dBFS with silences of 0.6-3 s every 8-40 s.
+    Returns (frames uint8 [nf, h, w, 3], pcm int16 [nf * sr, 1], frame_times fp64 [nf])."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    frames = torch.empty((nf, h, w, 3), dtype=torch.uint8, device=device)
+    f0 = 0
+    while f0 < nf:
+        length = int(torch.randint(5, 61, (1,), generator=g, device=device).item())
+        m = min(length, nf - f0)
+        yy = torch.linspace(0, 6.28, h, device=device)[:, None, None]
+        xx = torch.linspace(0, 6.28, w, device=device)[None, :, None]
+        ph = torch.rand((1, 1, 3), generator=g, device=device) * 6.28
+        fr = torch.rand((2,), generator=g, device=device) * 3 + 0.5
+        field = 128 + 40 * torch.sin(fr[0] * xx + ph) + 40 * torch.cos(fr[1] * yy + ph)
+        noisy = field[None] + 2.0 * torch.randn((m, h, w, 3), generator=g, device=device)
+        frames[f0:f0 + m] = noisy.round().clamp(0, 255).to(torch.uint8)
+        f0 += m
+    ns = nf * sr
+    pcm = (torch.randn((ns, 1), generator=g, device=device) * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
+    t_s = 0
+    while True:
+        t_s += int(torch.randint(8, 41, (1,), generator=g, device=device).item())
+        if t_s >= nf - 3:
+            break
+        ln = int((0.6 + 2.4 * torch.rand((1,), generator=g, device=device).item()) * sr)
+        pcm[t_s * sr:t_s * sr + ln] = (pcm[t_s * sr:t_s * sr + ln].float() * 1e-3).round().to(torch.int16)
+        t_s += 3
+    ft = torch.arange(nf, dtype=torch.float64, device=device)
+    return frames, pcm, ft

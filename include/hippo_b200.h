@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HIPPO_ABI_VERSION 1
+#define HIPPO_ABI_VERSION 2
 
 typedef int32_t hippo_status;
 #define HIPPO_OK           0
@@ -111,6 +111,37 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
                                 const uint64_t* after_key,
                                 int64_t* out_idx, float* out_score, uint64_t* out_key,
                                 void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Search straight over the caller's rows -- the drop-in signature of vo:151-188 hands the (N, D)
+ * feature array in with every call, in fp32 (fresh features) or fp64 (ThetaEvents reloaded from
+ * JSON, hm:391).  One streaming pass, no bank: dot product and row norm from the same registers,
+ * accumulated in fp64, rounded once to the arrays' own precision, then dot / (|b| * |a|) in the
+ * operation order of vo:182 (fp32 IEEE chain when rows and query are both fp32, fp64 otherwise,
+ * as NumPy promotes).  Nothing is rounded to bf16 on this path.
+ *   rows      [n, d] HIPPO_F32 / HIPPO_F64, row stride `ld` elements (any d >= 1)
+ *   q         [d] HIPPO_F32 / HIPPO_F64
+ *   out_*     as hippo_topk_single (out_score is the fp32 rounding of the score; hippo_rescore
+ *             returns the winners' scores in fp64)
+ */
+size_t       hippo_topk_rows_workspace_bytes(int64_t n, int32_t d, int32_t k);
+hippo_status hippo_topk_rows(const void* rows, int32_t dtype, int64_t n, int32_t d, int64_t ld,
+                             const void* q, int32_t q_dtype, int32_t k, int64_t row_base,
+                             const uint64_t* after_key,
+                             int64_t* out_idx, float* out_score, uint64_t* out_key,
+                             void* ws, size_t ws_bytes, void* stream);
+/*
+ * Exact second stage behind the bf16 searches: the same expression for `kc` candidate rows per
+ * query, from the ORIGINAL fp32 / fp64 rows (one warp per candidate).  cand_idx holds GLOBAL row
+ * numbers (rows [row_base, row_base + n) are local; -1 or a foreign row yields key 0).
+ *   out_key    optional [nq, kc] uint64 order keys of the exact scores (feed hippo_topk_merge
+ *              with nparts = 1 to re-rank)
+ *   out_score  optional [nq, kc] fp64 exact scores
+ */
+hippo_status hippo_rescore(const void* rows, int32_t dtype, int64_t n, int32_t d, int64_t ld,
+                           int64_t row_base, const void* q, int32_t q_dtype, int32_t nq,
+                           const int64_t* cand_idx, int32_t kc,
+                           uint64_t* out_key, double* out_score, void* stream);
 
 /*
  * Merge per-shard results: keys [nparts, nq, k_in] packed order keys (as written to
@@ -206,6 +237,20 @@ hippo_status hippo_consolidate(const float* feats, int64_t n, int32_t d, float g
                                float band_exact, float band_inexact,
                                int64_t* out_keep, int32_t* out_count, int32_t* out_stats,
                                void* ws, size_t ws_bytes, void* stream);
+/*
+ * The same with explicit sizing: `band_rows` rows per band (0 = default 8,192; rounded to 512) and
+ * room for `uncertain_cap` near-threshold pairs per band (0 = default 64 * (band + 1024) + 2^20).
+ * out_stats[1] != 0 reports that a band produced more near-threshold pairs than fit; the pairs
+ * beyond the capacity kept their tensor-core decision, so the caller must call again with a larger
+ * capacity (the Python wrapper does) before trusting the result.
+ */
+size_t       hippo_consolidate_ex_workspace_bytes(int64_t n, int32_t d, int32_t band_rows,
+                                                  int64_t uncertain_cap);
+hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, float gamma,
+                                  float band_exact, float band_inexact,
+                                  int32_t band_rows, int64_t uncertain_cap,
+                                  int64_t* out_keep, int32_t* out_count, int32_t* out_stats,
+                                  void* ws, size_t ws_bytes, void* stream);
 
 /* ---- temporal pattern separation ---------------------------------------- */
 /*

@@ -204,3 +204,31 @@ def test_small_bands_many_handoffs(cuda_device, monkeypatch, band, kind):
         else:
             ok, why = O.greedy_valid_under_tolerance(feats, kept, gamma)
             assert ok, why
+
+
+def test_recheck_overflow_is_detected_and_retried(cuda_device):
+    """One tight cluster of rows whose mutual similarities all sit inside the bf16 trust band around gamma: the
+    near-threshold list of a small capacity overflows (stats[1]), the device entry reports it, and the host
+    wrappers repeat the call with a larger list instead of returning tensor-core decisions."""
+    from hippomm_b200 import RecheckOverflow, checked_key_frames, select_key_frames
+    from hippomm_b200.consolidation import select_key_frames_device
+
+    rng = np.random.default_rng(123)
+    n, d = 3000, 1024
+    base = rng.standard_normal(d)
+    base /= np.linalg.norm(base)
+    # sim(i, j) = 1 / (1 + s^2) in expectation = 0.9 for s^2 = 1/9: every pair hovers around gamma
+    noise = rng.standard_normal((n, d)) / np.sqrt(d) * (1.0 / 3.0)
+    feats = (base[None, :] + noise).astype(np.float32)
+    fd = torch.from_numpy(feats).to(cuda_device)
+    _, _, stats = select_key_frames_device(fd, 0.9, uncertain_cap=1000)
+    assert int(stats[1].item()) == 1                                      # reported, not silent
+    ref, moat = O.select_key_frames_blocked(feats, 0.9, with_moat=True)
+    got = checked_key_frames(fd, 0.9, uncertain_cap=1000).cpu().numpy()   # retried with room for all pairs
+    if moat > 1e-6:
+        assert np.array_equal(got, ref)
+    else:
+        ok, why = O.greedy_valid_under_tolerance(feats, got, 0.9, tol=1e-6)
+        assert ok, why
+    assert np.array_equal(select_key_frames(feats, None, 0.9), got)
+    assert issubclass(RecheckOverflow, RuntimeError)

@@ -227,3 +227,100 @@ def test_row_base_and_merge(cuda_device, lib):
     torch.cuda.synchronize()
     assert torch.equal(oi, fi) and torch.equal(ok, fk)
     assert torch.equal(os_.view(torch.int32), fs.view(torch.int32))
+
+
+def test_dropin_is_exact_on_config1(cuda_device):
+    """The drop-in signature (host arrays in, NumPy out) never rounds the rows to bf16: on config 1's video-like
+    fp32 bank the top-5 ROWS AND ORDER equal the unmodified reference's committed outputs for all 64 queries
+    (neighbouring frames score within 1e-4 of each other; the bf16 bank alone swaps some of them)."""
+    from hippomm_b200 import MemoryBank, top_k_cosine_similarity
+
+    bank_h, queries = cases.search_config1()
+    g = cases.golden()
+    for qi in range(len(queries)):
+        idx, sim = top_k_cosine_similarity(queries[qi], bank_h, 5)
+        assert idx.dtype == np.int64 and sim.dtype == np.float32
+        assert np.array_equal(idx, g["search_c1_idx"][qi]), f"q{qi}: {idx} vs {g['search_c1_idx'][qi]}"
+        assert np.max(np.abs(sim - g["search_c1_sim"][qi])) < 5e-7
+    # the persistent bank reaches the same answer through exact=True (bf16 candidates, fp32 re-scoring)
+    bank = MemoryBank.from_rows(bank_h, keep_rows=True)
+    for path in ("single", "batched"):
+        idx, sim = bank.search(queries, 5, path=path, exact=True)
+        assert bank.exact_complete
+        assert np.array_equal(idx.cpu().numpy(), g["search_c1_idx"])
+        assert np.max(np.abs(sim.cpu().numpy() - g["search_c1_sim"])) < 5e-7
+    with pytest.raises(ValueError):
+        MemoryBank.from_rows(bank_h).search(queries, 5, exact=True)       # no original rows kept
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 3, 1), (7, 5, 7), (100, 130, 40), (1000, 1024, 10), (513, 2048, 16)])
+@pytest.mark.parametrize("bdt,qdt", [(np.float32, np.float32), (np.float64, np.float32), (np.float64, np.float64),
+                                     (np.float32, np.float64)])
+def test_rows_path_dtypes_and_shapes(cuda_device, n, d, k, bdt, qdt):
+    """hippo_topk_rows over fp32 / fp64 rows with fp32 / fp64 queries, dimensions that are not multiples of 4,
+    k beyond HIPPO_TOPK_MAX (cursor paging): rows, order and result dtype as NumPy's promotion rules give them
+    (vo:178-185), scores to the precision of the arrays."""
+    from hippomm_b200 import cosine_similarity, top_k_cosine_similarity
+
+    rng = np.random.default_rng(n * 131 + d)
+    b = rng.standard_normal((n, d)).astype(bdt)
+    q = rng.standard_normal(d).astype(qdt)
+    if n > 4:
+        b[3] = 0.0                                             # NaN score: first (vo:185)
+        b[4] = b[2]                                            # exact tie: lower row first
+    idx, sim = top_k_cosine_similarity(q, b, k)
+    ri, rs = O.top_k_cosine_similarity(q, b, k)
+    assert sim.dtype == rs.dtype and len(idx) == min(k, n)
+    tol = 1e-6 if (bdt == np.float32 and qdt == np.float32) else 1e-7
+    check_topk(idx, sim, ri, rs, tol=tol, what=f"rows n={n} d={d}")
+    if n > 4 and k >= 5:
+        assert idx[0] == 3 and np.isnan(sim[0])
+        li = list(idx)
+        if 2 in li and 4 in li:
+            assert li.index(4) == li.index(2) + 1
+    # a short vector pair: the case where a bf16 bank would miss by more than 1e-3
+    x = np.array([0.1234567, -2.3456789, 3.4567891], dtype=bdt)
+    assert abs(float(cosine_similarity(x, x)) - 1.0) < 1e-6
+    assert abs(float(cosine_similarity(x, q[:3].astype(qdt))) - float(O.cosine_similarity(x, q[:3].astype(qdt)))) < 1e-6
+
+
+def test_bank_cache_only_trusts_read_only_arrays(cuda_device):
+    """install(cache_banks=True): a device bank is reused only for arrays the caller marked read-only; a writeable
+    array is uploaded on every call, so an in-place edit between two calls is always seen."""
+    import hippomm_b200 as hb
+    from hippomm_b200 import vector_ops
+
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal((2000, 1024)).astype(np.float32)
+    q = b[1234] + 0.1 * rng.standard_normal(1024).astype(np.float32)
+    hb.set_bank_cache(4)
+    try:
+        i0, _ = hb.top_k_cosine_similarity(q, b, 3)
+        assert i0[0] == 1234 and len(vector_ops._bank_cache) == 0          # writeable: never cached
+        b[1234] = -b[1234]                                                 # one row edited in place
+        i1, _ = hb.top_k_cosine_similarity(q, b, 3)
+        assert i1[0] != 1234
+        ri, _ = O.top_k_cosine_similarity(q, b, 3)
+        assert np.array_equal(i1, ri)
+        b.flags.writeable = False
+        i2, _ = hb.top_k_cosine_similarity(q, b, 3)
+        assert len(vector_ops._bank_cache) == 1 and np.array_equal(i2, ri)
+        bank = next(iter(vector_ops._bank_cache.values()))[2]
+        i3, _ = hb.top_k_cosine_similarity(q, b, 3)
+        assert next(iter(vector_ops._bank_cache.values()))[2] is bank and np.array_equal(i3, ri)
+        v = b[:1000]                                                       # read-only view of a read-only base: fine
+        hb.top_k_cosine_similarity(q, v, 3)
+        assert len(vector_ops._bank_cache) == 2
+        w = np.array(b)                                                    # writeable copy, and a read-only VIEW of it
+        wv = w[:500]
+        wv.flags.writeable = False
+        hb.top_k_cosine_similarity(q, wv, 3)
+        assert len(vector_ops._bank_cache) == 2                            # its base can still be edited: not cached
+        hb.invalidate_bank_cache(b)
+        assert len(vector_ops._bank_cache) == 1
+        del v
+        import gc
+        gc.collect()
+        assert len(vector_ops._bank_cache) == 0                            # entries die with their arrays
+    finally:
+        hb.set_bank_cache(0)

@@ -98,6 +98,11 @@ def test_audio_levels_match_reference_outputs(cuda_device):
     assert abs(compute_audio_level(stereo, 16000) - g["audio_level_stereo"][0]) < DB_TOL
     assert compute_audio_level(np.zeros(100), 16000) == -100
     assert compute_audio_level(x64[:8000].reshape(-1, 1), 16000) == pytest.approx(g["audio_levels"][0], abs=DB_TOL)
+    # integer samples: taken at face value by default (what hm:995-998 computes for a 2-D integer array),
+    # read as PCM k / 32768 only on request
+    raw = pcm[:8000].reshape(-1, 1)
+    assert abs(compute_audio_level(raw, 16000) - O.compute_audio_level(raw)) < DB_TOL
+    assert compute_audio_level(raw, 16000, int16_pcm=True) == pytest.approx(g["audio_levels"][0], abs=DB_TOL)
     # ragged length, stereo, through the generic pyramid kernel
     st = torch.from_numpy(np.ascontiguousarray(np.stack([x64[:100003], x64[7:100010]], axis=1))).to(cuda_device)
     pyr = audio_energy_device(st)
@@ -142,11 +147,18 @@ def test_segment_edge_cases(cuda_device):
     ss = O.adjacent_ssim(frames[:60])
     want = O.segment_boundaries(ss, times, x.reshape(-1, 1), 16000)
     assert [(s.start_time, s.end_time) for s in segs] == want
-    # int16 input on the device side gives the same boundaries as the float64 the reference sees
-    segs16 = segment_sequence(None, None, cases.audio_case()[: 120 * 16000], 16000)
+    # int16 PCM on the device side (opt-in) gives the same boundaries as the float64 the reference sees from sf.read
+    segs16 = segment_sequence(None, None, cases.audio_case()[: 120 * 16000], 16000, int16_pcm=True)
     x120 = cases.audio_case()[: 120 * 16000].astype(np.float64) / 32768.0
     want = O.segment_boundaries(None, None, x120, 16000)
     assert [(s.start_time, s.end_time) for s in segs16] == want
+    # without the opt-in, integer samples are taken at face value like the reference's NumPy arithmetic does
+    # (levels ~ +70 dB: nothing is below -40 dB, every segment runs to max_segment_duration)
+    k2 = cases.audio_case()[: 120 * 16000].reshape(-1, 1)
+    segs_raw = segment_sequence(None, None, k2, 16000)
+    want_raw = O.segment_boundaries(None, None, k2, 16000)
+    assert [(s.start_time, s.end_time) for s in segs_raw] == want_raw
+    assert want_raw != want
 
 
 def test_one_hour_stream_against_oracle(cuda_device):
@@ -157,7 +169,7 @@ def test_one_hour_stream_against_oracle(cuda_device):
     frames, _ = synth.frame_stream(21, 3600, 64, 64)
     pcm = synth.audio_stream_int16(22, 3600 * 16000)
     times = cases.frame_times(3600)
-    segs = segment_sequence(frames, times, pcm.reshape(-1, 1), 16000)
+    segs = segment_sequence(frames, times, pcm.reshape(-1, 1), 16000, int16_pcm=True)
     ss = O.adjacent_ssim(frames)
     x = pcm.astype(np.float64) / 32768.0
     want = O.segment_boundaries(ss, times, x.reshape(-1, 1), 16000)
@@ -256,7 +268,7 @@ def test_audio_scan_near_the_threshold(cuda_device, sr, dtype, nch):
     else:
         given = seen = x
     for thresholds in ({}, {"max_segment_duration": 45.0, "min_segment_duration": 3.0}):
-        segs = segment_sequence(None, None, given, sr, **thresholds)
+        segs = segment_sequence(None, None, given, sr, int16_pcm=(dtype == "i16"), **thresholds)
         want = O.segment_boundaries(None, None, seen, sr, **thresholds)
         assert [(s.start_time, s.end_time) for s in segs] == want
         assert len(want) > 3
