@@ -67,12 +67,13 @@ def to_device(a, device: torch.device, dtype: torch.dtype | None = None) -> torc
         return t.to(device, non_blocking=True).contiguous()
     arr = np.ascontiguousarray(a)
     if not arr.flags.writeable:          # read-only arrays are only ever read here; torch just cannot express that
-        arr = arr.view()
-        try:
-            arr.flags.writeable = True
-        except ValueError:               # a buffer that really is read-only (bytes, mmap): copy
-            arr = np.array(arr)
-    t = torch.from_numpy(arr)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(arr)
+    else:
+        t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     if t.numel() * t.element_size() >= (1 << 20):

@@ -94,6 +94,7 @@ SIGNATURES = {
     "hippo_audio_energy": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P]),
     "hippo_audio_levels": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "hippo_segment_boundaries": (_I32, [_P, _I32, _F64, _F64, _F64, _F64, _P]),
+    "hippo_segment_boundaries_resume": (_I32, [_P, _I32, _P, _I64, _I32, _F64, _F64, _F64, _F64, _P]),
 }
 
 _lib = None

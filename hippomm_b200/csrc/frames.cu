@@ -137,7 +137,7 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 constexpr int kSsimThreads = 256;
 constexpr int kSsimWarps = kSsimThreads / 32;
 constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
-constexpr int kSsimBand = 56;                  // window rows per band
+constexpr int kSsimBand = 112;                 // window rows per band (6 halo rows per band: 5% at 112, 11% at 56)
 
 // Packed fp32 pairs (sm_100 f32x2 arithmetic): two IEEE round-to-nearest results per instruction.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_kernel(
   // window is fetched for the next step; kSse: this warp owns the row for the squared error.  The phases below
   // call it with compile-time flags, so the steady state carries no per-row predicates: the only data-dependent
   // address is the next row, clamped to the frame (its value is dead in the last step of a frame's last band).
-  static_assert(kSsimBand + 6 <= 64, "sqe / cr hold at most 64 rows x 4 bytes x 2 x 255^2 < 2^32 without a flush");
+  static_assert(kSsimBand + 6 <= 4096, "sqe / cr hold rows x 4 bytes x 2 x 255^2 < 2^32 without a flush: at most 8,256 rows");
   auto ldrow = [&](const uint8_t* g, int r) -> uint32_t {
     return col_ok ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
   };

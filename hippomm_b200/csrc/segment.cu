@@ -144,9 +144,15 @@ __device__ __forceinline__ int window_class(const double* __restrict__ e512, int
   return 2;       // includes NaN sums
 }
 
+// Resumable form (states != nullptr): the chain is carried across launches in `states[si]`, and a launch that is not
+// the final one only takes the segments whose window [current_start, current_end] is covered by the first
+// `frames_ready` frames (their adjacent-pair SSIMs are final) -- so the boundary chain of a stream can run under the
+// SSIM kernels of its later frames, one launch per chunk of frames, with no cross-kernel waiting anywhere.
 __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_stream_desc* __restrict__ streams,
                                                                  int nstreams, double max_dur, double min_dur,
                                                                  double ssim_thr, double db_thr,
+                                                                 hippo_segment_state* __restrict__ states,
+                                                                 int64_t frames_ready, int final_pass,
                                                                  unsigned long long* dbg) {
   extern __shared__ double s_stage[];          // [kStageFrames] frame times, [kStageFrames] ssim
   // per-segment results, triple-buffered so that ONE barrier per segment suffices: segment k uses set k % 3,
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   if (si >= nstreams) return;
   const hippo_stream_desc S = streams[si];
 
+  if (states != nullptr && states[si].done) return;
   const bool has_video = S.frame_times != nullptr && S.nframes > 0;   // `if video_frames and frame_times`
   const bool has_audio = S.pcm != nullptr && S.sample_rate != 0.0;    // `audio_data is not None and audio_sample_rate`
   const double sr = S.sample_rate;
@@ -181,7 +188,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     stage(S.frame_times, s_stage, nf);
     ftimes = s_stage;
     if (S.ssim != nullptr) {
-      stage(S.ssim, s_stage + kStageFrames, nf - 1);
+      const int64_t pairs = (states != nullptr && !final_pass) ? (frames_ready - 1 < nf - 1 ? frames_ready - 1 : nf - 1) : nf - 1;
+      stage(S.ssim, s_stage + kStageFrames, pairs > 0 ? pairs : 0);
       ssim = s_stage + kStageFrames;
     }
   }
@@ -192,7 +200,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   double total;
   if (has_video) total = ftimes[nf - 1] - ftimes[0];
   else if (has_audio) total = (double)S.ns / sr;
-  else { if (tid == 0) *S.out_count = 0; return; }
+  else {
+    if (tid == 0) { *S.out_count = 0; if (states != nullptr) states[si].done = 1; }
+    return;
+  }
 
   const double pow_thr = pow(10.0, db_thr / 10.0);
   const int64_t w = has_audio ? (int64_t)(0.5 * sr) : 0;   // hm:1066; the host rejects w < 1 like range() does
@@ -200,15 +211,21 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   const int vt = tid - kSegWindows;                  // video lane: threads 64..255
   const double bound_w_lo = pow_thr * (double)w * (1.0 - 1e-9), bound_w_hi = pow_thr * (double)w * (1.0 + 1e-9);
   int count = 0;
-  bool overflow = false;
+  bool overflow = false, suspended = false;
   int64_t hint = 0;                                  // first frame with t >= current_start so far
   double cs = 0.0;                                   // hm:1034
+  if (states != nullptr) { cs = states[si].current_start; hint = states[si].hint; count = states[si].count; }
+  const int count0 = count;
+  // a pass that is not final may only look at frames below frames_ready; it needs one of them BEYOND the window
+  const bool gated = states != nullptr && !final_pass && has_video;
+  const double t_ready = (gated && frames_ready > 0) ? ftimes[(frames_ready < nf ? frames_ready : nf) - 1] : 0.0;
   long long t_pre = 0, t_bar = 0, t_tail = 0, n_exact = 0;
   while (cs < total) {                               // hm:1036
     const long long c0 = dbg ? clock64() : 0;
-    const int set = count % 3;
+    if (gated && !(frames_ready > 0 && t_ready > py_min(cs + max_dur, total))) { suspended = true; break; }
+    const int set = (count - count0) % 3;
     if (tid == kSegThreads - 1) {                    // a thread of the video group: off the audio threads' critical path
-      const int nx = (count + 1) % 3;
+      const int nx = (count - count0 + 1) % 3;
       s_lo[nx] = -1; s_vpick[nx] = -1; s_apick[nx] = 0x7fffffff; s_amb[nx] = 0x7fffffff;
     }
     const double ce = py_min(cs + max_dur, total);   // hm:1038
@@ -309,16 +326,22 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     cs = opt;                                        // hm:1111
     if (dbg) { const long long c4 = clock64(); t_pre += c2 - c0; t_bar += c3 - c2; t_tail += c4 - c3; }
   }
-  if (tid == 0) *S.out_count = overflow ? -1 : count;
+  if (tid == 0) {
+    *S.out_count = overflow ? -1 : count;
+    if (states != nullptr) {
+      states[si].current_start = cs; states[si].hint = hint; states[si].count = count;
+      states[si].done = (suspended && !overflow) ? 0 : 1;
+    }
+  }
   if (dbg && tid == 0 && si == 0) { dbg[0] = t_pre; dbg[1] = t_bar; dbg[2] = t_tail; dbg[3] = n_exact; dbg[6] = count; }
 }
 
 }  // namespace hippo
 
-extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t nstreams,
-                                                 double max_segment_duration, double min_segment_duration,
-                                                 double frame_similarity_threshold,
-                                                 double audio_silence_threshold, void* stream) {
+static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nstreams, double max_segment_duration,
+                                   double min_segment_duration, double frame_similarity_threshold,
+                                   double audio_silence_threshold, hippo_segment_state* states, int64_t frames_ready,
+                                   int final_pass, void* stream) {
   using namespace hippo;
   HIPPO_REQUIRE(nstreams >= 0, "hippo_segment_boundaries: nstreams < 0");
   if (nstreams == 0) return HIPPO_OK;
@@ -326,12 +349,13 @@ extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* stream
   hippo_status st = check_arch();
   if (st != HIPPO_OK) return st;
   const size_t smem = (size_t)2 * kStageFrames * sizeof(double);
-  HIPPO_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr = false;
+  if (!attr) { HIPPO_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   unsigned long long* dbg = nullptr;
   if (getenv("HIPPO_SEG_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
   segment_kernel<<<nstreams, kSegThreads, smem, (cudaStream_t)stream>>>(
       streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
-      audio_silence_threshold, dbg);
+      audio_silence_threshold, states, frames_ready, final_pass, dbg);
   if (dbg) {
     unsigned long long h[8];
     cudaStreamSynchronize((cudaStream_t)stream);
@@ -342,4 +366,25 @@ extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* stream
   }
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
+}
+
+extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t nstreams,
+                                                 double max_segment_duration, double min_segment_duration,
+                                                 double frame_similarity_threshold,
+                                                 double audio_silence_threshold, void* stream) {
+  return launch_segment(streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
+                        audio_silence_threshold, nullptr, 0, 1, stream);
+}
+
+extern "C" hippo_status hippo_segment_boundaries_resume(const hippo_stream_desc* streams, int32_t nstreams,
+                                                        hippo_segment_state* states, int64_t frames_ready,
+                                                        int32_t final_pass, double max_segment_duration,
+                                                        double min_segment_duration,
+                                                        double frame_similarity_threshold,
+                                                        double audio_silence_threshold, void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(states != nullptr, "hippo_segment_boundaries_resume: null state table");
+  HIPPO_REQUIRE(frames_ready >= 0, "hippo_segment_boundaries_resume: frames_ready < 0");
+  return launch_segment(streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
+                        audio_silence_threshold, states, frames_ready, final_pass ? 1 : 0, stream);
 }

@@ -279,6 +279,67 @@ def pattern_separation_batch_device(streams, max_segment_duration: float, min_se
                                                frame_similarity_threshold, audio_silence_threshold, max_segments)
 
 
+def pattern_separation_host(frames, frame_times, pcm, sample_rate, max_segment_duration: float,
+                            min_segment_duration: float, frame_similarity_threshold: float,
+                            audio_silence_threshold: float, max_segments: int, chunk_frames: int = 384):
+    """Temporal pattern separation of ONE stream whose frames and samples sit in HOST memory (what a caller of
+    the reference has after decoding: hm:982-983 reads the frames from disk, bp:331-335 the samples).
+
+    frames: uint8 [nf, h, w, ch] CPU tensor (pinned memory makes the upload a plain DMA), pcm: [ns, nch] CPU tensor
+    (int16 PCM / float32 / float64) or None, frame_times: fp64 [nf] CPU or device tensor.  The frames are uploaded
+    in chunks of `chunk_frames` (+1 frame of overlap, so every adjacent pair lives in exactly one chunk) through two
+    device staging buffers on the copy stream; gray conversion + SSIM of chunk i run under the upload of chunk
+    i + 1, the samples follow last, then the boundary kernel.  Returns (bounds fp64 [max_segments, 2] device,
+    count int32 [1] device, ssim fp64 [nf - 1] device).  At 224 x 224 the pass is PCIe-bound (542 MB of frames)."""
+    from .bank import _copy_stream
+
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.is_cuda:
+        raise ValueError("frames must be a uint8 [n, h, w, ch] CPU tensor")
+    dev = _cuda.require_device()
+    nf = frames.shape[0]
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        copy = _copy_stream(dev)
+        copy.wait_stream(main)
+        ssim = torch.empty((max(nf - 1, 1),), dtype=torch.float64, device=dev)
+        mse = torch.empty((max(nf - 1, 1),), dtype=torch.float64, device=dev)
+        cf = max(2, int(chunk_frames))
+        stage = [torch.empty((min(cf, nf - 1) + 1,) + tuple(frames.shape[1:]), dtype=torch.uint8, device=dev)
+                 for _ in range(2)] if nf > 1 else []
+        up = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        for i, f0 in enumerate(range(0, nf - 1, cf)):
+            b = i & 1
+            f1 = min(nf - 1, f0 + cf)                      # frames [f0, f1] -> pairs f0 .. f1 - 1
+            m = f1 - f0 + 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(done[b])
+                stage[b][:m].copy_(frames[f0:f1 + 1], non_blocking=True)
+                up[b].record(copy)
+            main.wait_event(up[b])
+            frame_pair_scores_device(stage[b][:m], range_mode=0, out=(ssim[f0:], mse[f0:]))
+            done[b].record(main)
+        pcm_d = pyr = None
+        if pcm is not None:
+            with torch.cuda.stream(copy):
+                pcm_d = pcm.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            main.wait_event(ev)
+            pcm_d.record_stream(main)
+            if pcm_d.dim() == 1:
+                pcm_d = pcm_d.reshape(-1, 1)
+            pyr = audio_energy_device(pcm_d)
+        ft_d = frame_times.to(dev, torch.float64, non_blocking=True) if frame_times is not None else None
+        for st in stage:
+            st.record_stream(main)
+        bounds, count = segment_boundaries_device(ssim[: nf - 1] if nf > 1 else None, ft_d, pcm_d, pyr, sample_rate,
+                                                  max_segment_duration, min_segment_duration,
+                                                  frame_similarity_threshold, audio_silence_threshold, max_segments)
+    return bounds, count, ssim[: max(nf - 1, 0)]
+
+
 _side: dict = {}
 
 

@@ -324,6 +324,31 @@ hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t 
                                       double frame_similarity_threshold,
                                       double audio_silence_threshold, void* stream);
 
+/*
+ * The same state machine in resumable form, so that the boundary chain of a stream (sequential by
+ * nature: hm:1036 loops on current_start) can run UNDER the SSIM kernels of the stream's later
+ * frames.  `states[s]` (device memory, zero-filled before the first call) carries (current_start,
+ * frame hint, segments written) from launch to launch.  A launch with final_pass == 0 takes only the
+ * segments whose window [current_start, current_start + max] is covered by the first `frames_ready`
+ * frames of every stream (pairs p < frames_ready - 1 of `ssim` are final), then suspends; the launch
+ * with final_pass != 0 runs the chain to the end.  The segments written are identical to one
+ * hippo_segment_boundaries call on the complete inputs.  Audio (pcm, pyramid) must be complete from
+ * the first launch on.
+ */
+typedef struct hippo_segment_state {
+  double  current_start;
+  int64_t hint;
+  int32_t count;
+  int32_t done;
+} hippo_segment_state;
+
+hippo_status hippo_segment_boundaries_resume(const hippo_stream_desc* streams, int32_t nstreams,
+                                             hippo_segment_state* states, int64_t frames_ready,
+                                             int32_t final_pass,
+                                             double max_segment_duration, double min_segment_duration,
+                                             double frame_similarity_threshold,
+                                             double audio_silence_threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
