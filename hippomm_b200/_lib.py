@@ -57,6 +57,12 @@ class StreamDesc(C.Structure):
     ]
 
 
+class SegmentState(C.Structure):
+    """hippo_segment_state"""
+
+    _fields_ = [("current_start", C.c_double), ("hint", C.c_int64), ("count", C.c_int32), ("done", C.c_int32)]
+
+
 _P = C.c_void_p
 _I32 = C.c_int32
 _I64 = C.c_int64
@@ -81,6 +87,10 @@ SIGNATURES = {
     "hippo_topk_merge": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hippo_topk_exchange_bytes": (_SZ, [_I32, _I32, _I32]),
     "hippo_topk_exchange_merge": (_I32, [_P, _I32, _I32, _I32, _P, _SZ, _I32, _I32, C.c_uint32, _P, _P, _P, _P]),
+    "hippo_topk_batched_sharded": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I32, _I64, _P, _P, _SZ, _I32, _I32, C.c_uint32,
+                                          _P, _P, _P, _P, _SZ, _P]),
+    "hippo_topk_single_sharded": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I64, _P, _P, _SZ, _I32, _I32, C.c_uint32,
+                                         _P, _P, _P, _P, _SZ, _P]),
     "hippo_scores_single": (_I32, [_P, _P, _I64, _I32, _P, _P, _P]),
     "hippo_topk_segmented_workspace_bytes": (_SZ, [_I64]),
     "hippo_topk_segmented": (_I32, [_P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),

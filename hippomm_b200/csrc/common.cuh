@@ -87,6 +87,48 @@ __device__ __forceinline__ void topk_insert(uint64_t* list, int k, uint64_t key)
   list[j] = key;
 }
 
+// ------------------------------------------------- warp-level k-way selection ----
+// Every lane keeps the best k (<= 16) of the keys it has seen in a sorted register list (compare-swap chain with
+// static indices: no local memory); warp_select_best then pops the global maximum k times.  Keys are unique per
+// row, 0 = empty.
+constexpr int kLaneList = HIPPO_TOPK_MAX;
+__device__ __forceinline__ void lane_list_clear(uint64_t (&L)[kLaneList]) {
+#pragma unroll
+  for (int i = 0; i < kLaneList; ++i) L[i] = 0;
+}
+__device__ __forceinline__ void lane_list_insert(uint64_t (&L)[kLaneList], int k, uint64_t key) {
+  uint64_t v = key;
+#pragma unroll
+  for (int i = 0; i < kLaneList; ++i) {
+    if (i < k) {
+      const bool gt = v > L[i];
+      const uint64_t lo = gt ? L[i] : v;
+      L[i] = gt ? v : L[i];
+      v = lo;
+    }
+  }
+}
+// Returns, in lane r < k, the r-th best key over all lanes' lists (0 when fewer than r + 1 exist).
+__device__ __forceinline__ uint64_t warp_select_best(uint64_t (&L)[kLaneList], int k, int lane) {
+  uint64_t mine = 0;
+  for (int r = 0; r < k; ++r) {
+    uint64_t best = L[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == r) mine = best;
+    if (best == 0) break;                       // uniform: nothing left anywhere
+    if (L[0] == best) {                         // unique keys: exactly one lane pops
+#pragma unroll
+      for (int i = 0; i + 1 < kLaneList; ++i) L[i] = L[i + 1];
+      L[kLaneList - 1] = 0;
+    }
+  }
+  return mine;
+}
+
 // ------------------------------------------------------------ warp helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

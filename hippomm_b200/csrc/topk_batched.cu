@@ -1,6 +1,7 @@
 // hippo_topk_batched: nq queries against the bank in one tcgen05 pass (see sim_tc.cu).
 // Reference: nq sequential calls of top_k_cosine_similarity (vo:151-188).
 #include "common.cuh"
+#include "exchange.cuh"
 #include "sim_tc.cuh"
 
 namespace hippo {
@@ -9,8 +10,8 @@ namespace hippo {
 bool topk_few_supported(int d, int nq);
 size_t topk_few_part_elems(int nq, int k);
 hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, const float* q, int nq, int k,
-                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int64_t* out_idx,
-                             float* out_score, uint64_t* out_key, cudaStream_t s);
+                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int* nparts_out,
+                             cudaStream_t s);
 
 struct BatchedLayout {
   __nv_bfloat16* qbf;
@@ -48,41 +49,31 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   return L;
 }
 
-}  // namespace hippo
-
-extern "C" {
-
-size_t hippo_topk_batched_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k) {
-  if (n < 0 || d <= 0 || nq <= 0 || k <= 0) return 256;
-  return hippo::batched_layout(nullptr, 0, n, d, nq, k).bytes;
-}
-
-hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, int32_t d, const float* q,
-                                int32_t nq, int32_t k, int64_t row_base, const uint64_t* after_key,
-                                int64_t* out_idx, float* out_score, uint64_t* out_key, void* ws,
-                                size_t ws_bytes, void* stream) {
-  using namespace hippo;
-  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "hippo_topk_batched: need d %% 64 == 0 (d=%d)", d);
-  HIPPO_REQUIRE(nq >= 0, "hippo_topk_batched: nq < 0");
-  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "hippo_topk_batched: k=%d outside 1..%d", k, HIPPO_TOPK_MAX);
-  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll,
-                "hippo_topk_batched: global row numbers must stay below 2^32-1");
-  if (nq == 0) return HIPPO_OK;
-  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "hippo_topk_batched: null pointer");
+// The local search up to (not including) the merge of the per-split lists: *part_out = [nparts][nq][k] order keys.
+static hippo_status batched_parts(const void* bank, const float* norm, int64_t n, int32_t d, const float* q, int32_t nq,
+                                  int32_t k, int64_t row_base, const uint64_t* after_key, void* ws, size_t ws_bytes,
+                                  void* stream, uint64_t** part_out, int* nparts_out, const char* who) {
+  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "%s: need d %% 64 == 0 (d=%d)", who, d);
+  HIPPO_REQUIRE(nq >= 1, "%s: nq < 1", who);
+  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "%s: k=%d outside 1..%d", who, k, HIPPO_TOPK_MAX);
+  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll, "%s: global row numbers must stay below 2^32-1", who);
+  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "%s: null pointer", who);
   hippo_status st = check_arch();
   if (st != HIPPO_OK) return st;
   cudaStream_t s = (cudaStream_t)stream;
   BatchedLayout L = batched_layout(ws, ws_bytes, n, d, nq, k);
   if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
-    set_error("hippo_topk_batched: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
+    set_error("%s: workspace of %zu bytes needed (256-byte aligned), got %zu", who, L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;
   }
+  *part_out = L.part;
   if (n == 0) {
     HIPPO_CUDA(cudaMemsetAsync(L.part, 0, (size_t)nq * k * 8, s));
-    return hippo_topk_merge(L.part, 1, nq, k, k, out_idx, out_score, out_key, stream);
+    *nparts_out = 1;
+    return HIPPO_OK;
   }
   if (topk_few_supported(d, nq))   // two queries: one GEMV pass with two accumulators per row (topk_single.cu)
-    return topk_few_launch(bank, norm, n, q, nq, k, row_base, after_key, L.part, out_idx, out_score, out_key, s);
+    return topk_few_launch(bank, norm, n, q, nq, k, row_base, after_key, L.part, nparts_out, s);
   HIPPO_CUDA(cudaMemsetAsync(L.thr_ord, 0, L.clear_words * 4, s));
   // queries -> bf16 + |a| (same pass the bank went through)
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
@@ -106,9 +97,51 @@ hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, 
   a.counters = L.counters;
   a.progress = L.progress;
   a.splits = L.splits;
-  st = tc_topk_launch(a, s);
+  *nparts_out = 2 * L.splits;
+  return tc_topk_launch(a, s);
+}
+
+}  // namespace hippo
+
+extern "C" {
+
+size_t hippo_topk_batched_workspace_bytes(int64_t n, int32_t d, int32_t nq, int32_t k) {
+  if (n < 0 || d <= 0 || nq <= 0 || k <= 0) return 256;
+  return hippo::batched_layout(nullptr, 0, n, d, nq, k).bytes;
+}
+
+hippo_status hippo_topk_batched(const void* bank, const float* norm, int64_t n, int32_t d, const float* q,
+                                int32_t nq, int32_t k, int64_t row_base, const uint64_t* after_key,
+                                int64_t* out_idx, float* out_score, uint64_t* out_key, void* ws,
+                                size_t ws_bytes, void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(nq >= 0, "hippo_topk_batched: nq < 0");
+  if (nq == 0) return HIPPO_OK;
+  uint64_t* part = nullptr;
+  int nparts = 0;
+  hippo_status st = batched_parts(bank, norm, n, d, q, nq, k, row_base, after_key, ws, ws_bytes, stream, &part, &nparts,
+                                  "hippo_topk_batched");
   if (st != HIPPO_OK) return st;
-  return hippo_topk_merge(L.part, 2 * L.splits, nq, k, k, out_idx, out_score, out_key, stream);
+  return hippo_topk_merge(part, nparts, nq, k, k, out_idx, out_score, out_key, stream);
+}
+
+hippo_status hippo_topk_batched_sharded(const void* bank, const float* norm, int64_t n, int32_t d, const float* q,
+                                        int32_t nq, int32_t k, int64_t row_base, const uint64_t* after_key,
+                                        void* const* peer_bases, size_t buf_bytes, int32_t rank, int32_t world,
+                                        uint32_t epoch, int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                        void* ws, size_t ws_bytes, void* stream) {
+  using namespace hippo;
+  HIPPO_REQUIRE(nq >= 0, "hippo_topk_batched_sharded: nq < 0");
+  if (nq == 0) return HIPPO_OK;
+  uint64_t* part = nullptr;
+  int nparts = 0;
+  hippo_status st = batched_parts(bank, norm, n, d, q, nq, k, row_base, after_key, ws, ws_bytes, stream, &part, &nparts,
+                                  "hippo_topk_batched_sharded");
+  if (st != HIPPO_OK) return st;
+  // the per-split lists are merged inside the exchange kernel, just before its push phase: one launch for
+  // local merge + NVLink push + global merge
+  return exchange_launch(part, nparts, nq, k, k, peer_bases, buf_bytes, rank, world, epoch, out_idx, out_score, out_key,
+                         (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@
 // query staged in shared memory, reduces with shuffles, and keeps a warp-private top-k list
 // that only rows passing a threshold test ever touch.  Per-block lists are merged by a
 // selection pass; a second tiny kernel merges the per-block results.
-#include "common.cuh"
+#include "exchange.cuh"
 #include <cstdlib>
 
 namespace hippo {
@@ -42,11 +42,25 @@ __device__ __forceinline__ float filter_threshold(uint64_t kth_key, float an) {
   return lo - fabsf(lo) * 9.5367431640625e-07f - 1e-37f;    // 2^-20 relative slack
 }
 
-template <int CH>  // CH = d/256 when d is a multiple of 256 and <= 4*256; 0 = generic
+// Tail of the sharded single-query search, run by the LAST CTA of the GEMV to finish (ticket counter): merge of the
+// per-block lists, push of the k keys into every peer's gather buffer over NVLink, flag exchange, merge of the
+// world x k candidates -- the whole query is ONE launch per rank (GEMV, merge kernel and exchange kernel were three:
+// ~0.16 ms of a 0.36 ms shard pass at 8 GPUs).  world == 1 degenerates to the local merge.
+struct SingleTail {
+  uint32_t* ticket;                  // zero before the launch; the last CTA resets it
+  unsigned char* const* peer_bases;  // device array [world] (see hippo_topk_exchange_merge)
+  size_t slot_stride;
+  int rank, world;
+  uint32_t epoch;
+  int64_t* out_idx; float* out_score; uint64_t* out_key;
+};
+
+template <int CH, bool kFused>  // CH = d/256 when d is a multiple of 256 and <= 4*256; 0 = generic
 __global__ void __launch_bounds__(kSingleThreads, 2)
 topk_single_kernel(const __nv_bfloat16* __restrict__ bank, const float* __restrict__ norm, int64_t n,
                    int d, const float* __restrict__ q, int k, int64_t row_base,
-                   const uint64_t* __restrict__ after_key, uint64_t* __restrict__ part /*[grid][k]*/) {
+                   const uint64_t* __restrict__ after_key, uint64_t* __restrict__ part /*[grid][k]*/,
+                   const SingleTail tail) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // query, permuted so that a lane's two float4 loads are conflict free:
   // element e = c*256 + lane*8 + h*4 + j  ->  sq[((c*2 + h)*32 + lane)*4 + j]
@@ -178,6 +192,57 @@ topk_single_kernel(const __nv_bfloat16* __restrict__ bank, const float* __restri
       prev = b ? b : 0;  // once empty, stays empty
       if (b == 0) prev = 0;
     }
+  }
+  if constexpr (kFused) {
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) {
+      __threadfence();                                  // this CTA's list is visible before the ticket is taken
+      s_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // every warp merges its share of the gridDim.x * k candidates, warp 0 merges the warps' lists
+    uint64_t L[kLaneList];
+    lane_list_clear(L);
+    const int total = (int)gridDim.x * k;
+    for (int i = threadIdx.x; i < total; i += kSingleThreads) lane_list_insert(L, k, __ldcg(&part[i]));
+    uint64_t mine = warp_select_best(L, k, lane);
+    if (lane < k) lists[wid * k + lane] = mine;
+    __syncthreads();
+    if (wid != 0) return;
+    lane_list_clear(L);
+    for (int i = lane; i < kSingleWarps * k; i += 32) lane_list_insert(L, k, lists[i]);
+    mine = warp_select_best(L, k, lane);               // lane r < k: this rank's r-th best
+    if (tail.world > 1) {
+      const uint32_t par = tail.epoch & 1u;
+      if (lane < k)
+        for (int p = 0; p < tail.world; ++p)
+          xchg_slot(tail.peer_bases[p], par, tail.world, tail.rank, tail.slot_stride)[lane] = mine;
+      __threadfence_system();
+      __syncwarp();
+      if (lane < tail.world) {
+        uint32_t* flags = reinterpret_cast<uint32_t*>(tail.peer_bases[lane]);
+        st_release_sys(&flags[par * kXchgMaxWorld + tail.rank], tail.epoch);
+        const uint32_t* own_flags = reinterpret_cast<const uint32_t*>(tail.peer_bases[tail.rank]);
+        while (ld_acquire_sys(&own_flags[par * kXchgMaxWorld + lane]) != tail.epoch) __nanosleep(32);
+      }
+      __syncwarp();
+      __threadfence_system();
+      const uint64_t* gathered = xchg_slot(tail.peer_bases[tail.rank], par, tail.world, 0, tail.slot_stride);
+      lane_list_clear(L);
+      for (int i = lane; i < tail.world * k; i += 32) {
+        const int p = i / k, j = i - p * k;
+        lane_list_insert(L, k, __ldcg(&gathered[(size_t)p * tail.slot_stride + j]));
+      }
+      mine = warp_select_best(L, k, lane);
+    }
+    if (lane < k) {
+      if (tail.out_idx) tail.out_idx[lane] = mine ? (int64_t)key_row(mine) : -1;
+      if (tail.out_score) tail.out_score[lane] = mine ? key_score(mine) : 0.f;
+      if (tail.out_key) tail.out_key[lane] = mine;
+    }
+    if (lane == 0) *tail.ticket = 0;
   }
 }
 
@@ -352,9 +417,10 @@ bool topk_few_supported(int d, int nq) {
 }
 size_t topk_few_part_elems(int nq, int k) { return (size_t)sm_count() * 2 * (size_t)nq * (size_t)k; }
 
+// launches the GEMV only; *nparts_out receives the number of per-block lists in `part` ([nparts][nq][k])
 hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, const float* q, int nq, int k,
-                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int64_t* out_idx,
-                             float* out_score, uint64_t* out_key, cudaStream_t s) {
+                             int64_t row_base, const uint64_t* after_key, uint64_t* part, int* nparts_out,
+                             cudaStream_t s) {
   constexpr int NQ = 2;
   HIPPO_REQUIRE(nq == NQ, "topk_few_launch: nq=%d", nq);
   const size_t smem = (size_t)NQ * 1024 * 4 + (size_t)NQ * kFewWarps * k * 8;
@@ -364,10 +430,13 @@ hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, con
   if (want < grid) grid = (int)(want < 1 ? 1 : want);
   topk_few_kernel<NQ><<<grid, kFewThreads, smem, s>>>((const __nv_bfloat16*)bank, norm, n, q, nq, k, row_base, after_key, part);
   HIPPO_CUDA(cudaGetLastError());
-  return hippo_topk_merge(part, grid, nq, k, k, out_idx, out_score, out_key, (void*)s);
+  *nparts_out = grid;
+  return HIPPO_OK;
 }
 
-// keys [nparts, nq, k_in] -> best k per query; one warp per query.
+// keys [nparts, nq, k_in] -> best k per query; one warp per query.  ONE pass over the candidates: every lane
+// keeps the best k of its share in a sorted register list, then the warp pops the k global maxima (the previous
+// version rescanned all nparts * k_in candidates once per output rank: 76 us for 4,096 queries x 74 lists).
 __global__ void __launch_bounds__(128) topk_merge_kernel(const uint64_t* __restrict__ keys, int nparts,
                                                          int nq, int k_in, int k,
                                                          int64_t* __restrict__ out_idx,
@@ -376,6 +445,25 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const uint64_t* __restr
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq) return;
+  if (k <= kLaneList) {
+    uint64_t L[kLaneList];
+    lane_list_clear(L);
+    const int total = nparts * k_in;
+    for (int i = lane; i < total; i += 32) {
+      const int p = i / k_in, j = i - p * k_in;
+      const uint64_t c = keys[((size_t)p * nq + qi) * k_in + j];
+      lane_list_insert(L, k, c);
+    }
+    const uint64_t mine = warp_select_best(L, k, lane);
+    if (lane < k) {
+      const size_t o = (size_t)qi * k + lane;
+      if (out_idx) out_idx[o] = mine ? (int64_t)key_row(mine) : -1;
+      if (out_score) out_score[o] = mine ? key_score(mine) : 0.f;
+      if (out_key) out_key[o] = mine;
+    }
+    return;
+  }
+  // k beyond the register list (exact search merging many pages): selection by repeated scans
   uint64_t prev = ~0ull;
   for (int r = 0; r < k; ++r) {
     uint64_t best = 0;
@@ -421,7 +509,7 @@ size_t hippo_topk_single_workspace_bytes(int64_t n, int32_t d, int32_t k) {
   int sms = hippo::sm_count();
   if (sms <= 0) sms = 148;
   (void)n;
-  return hippo::align_up((size_t)sms * 2 * (size_t)(k > 0 ? k : 1) * 8, 256);
+  return hippo::align_up((size_t)sms * 2 * (size_t)(k > 0 ? k : 1) * 8 + 64, 256);   // per-block lists + the ticket
 }
 
 hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, int32_t k_in,
@@ -440,45 +528,93 @@ hippo_status hippo_topk_merge(const uint64_t* keys, int32_t nparts, int32_t nq, 
   return HIPPO_OK;
 }
 
+static hippo_status single_launch(const void* bank, const float* norm, int64_t n, int32_t d, const float* q, int32_t k,
+                                  int64_t row_base, const uint64_t* after_key, void* ws, size_t ws_bytes,
+                                  cudaStream_t s, const hippo::SingleTail* tail, int64_t* out_idx, float* out_score,
+                                  uint64_t* out_key, const char* who) {
+  using namespace hippo;
+  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "%s: need d %% 64 == 0 (d=%d)", who, d);
+  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "%s: k=%d outside 1..%d", who, k, HIPPO_TOPK_MAX);
+  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll, "%s: global row numbers must stay below 2^32-1", who);
+  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "%s: null pointer", who);
+  hippo_status st = check_arch();
+  if (st != HIPPO_OK) return st;
+  const int grid = single_grid(n);
+  if (ws == nullptr || ws_bytes < hippo_topk_single_workspace_bytes(n, d, k) || ((uintptr_t)ws & 255)) {
+    set_error("%s: workspace of %zu bytes needed (256-byte aligned)", who, hippo_topk_single_workspace_bytes(n, d, k));
+    return HIPPO_E_WORKSPACE;
+  }
+  uint64_t* part = (uint64_t*)ws;
+  const size_t smem = single_smem_bytes(d, k);
+  HIPPO_REQUIRE(smem <= 200 * 1024, "%s: d=%d too large", who, d);
+  const __nv_bfloat16* b = (const __nv_bfloat16*)bank;
+  if (tail == nullptr) {
+    if (n == 0) {
+      HIPPO_CUDA(cudaMemsetAsync(part, 0, (size_t)k * 8, s));
+      return hippo_topk_merge(part, 1, 1, k, k, out_idx, out_score, out_key, (void*)s);
+    }
+    const SingleTail none{};
+    if (d == 1024) {
+      static bool attr4 = false;
+      if (!attr4) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr4 = true; }
+      topk_single_kernel<4, false><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part, none);
+    } else {
+      static bool attr0 = false;
+      if (!attr0) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0 = true; }
+      topk_single_kernel<0, false><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part, none);
+    }
+    HIPPO_CUDA(cudaGetLastError());
+    return hippo_topk_merge(part, grid, 1, k, k, out_idx, out_score, out_key, (void*)s);
+  }
+  // fused tail: the ticket sits behind the per-block lists (sized for 2 CTAs per SM); an empty shard still takes part
+  // in the exchange (one CTA, every score list empty)
+  SingleTail t = *tail;
+  t.ticket = reinterpret_cast<uint32_t*>(part + (size_t)sm_count() * 2 * k);
+  HIPPO_CUDA(cudaMemsetAsync(t.ticket, 0, 4, s));
+  if (d == 1024) {
+    static bool attr4f = false;
+    if (!attr4f) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr4f = true; }
+    topk_single_kernel<4, true><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part, t);
+  } else {
+    static bool attr0f = false;
+    if (!attr0f) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0f = true; }
+    topk_single_kernel<0, true><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part, t);
+  }
+  HIPPO_CUDA(cudaGetLastError());
+  return HIPPO_OK;
+}
+
 hippo_status hippo_topk_single(const void* bank, const float* norm, int64_t n, int32_t d,
                                const float* q, int32_t k, int64_t row_base,
                                const uint64_t* after_key, int64_t* out_idx, float* out_score,
                                uint64_t* out_key, void* ws, size_t ws_bytes, void* stream) {
+  return single_launch(bank, norm, n, d, q, k, row_base, after_key, ws, ws_bytes, (cudaStream_t)stream, nullptr, out_idx,
+                       out_score, out_key, "hippo_topk_single");
+}
+
+hippo_status hippo_topk_single_sharded(const void* bank, const float* norm, int64_t n, int32_t d, const float* q,
+                                       int32_t k, int64_t row_base, const uint64_t* after_key,
+                                       void* const* peer_bases, size_t buf_bytes, int32_t rank, int32_t world,
+                                       uint32_t epoch, int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                       void* ws, size_t ws_bytes, void* stream) {
   using namespace hippo;
-  HIPPO_REQUIRE(n >= 0 && d > 0 && d % 64 == 0, "hippo_topk_single: need d %% 64 == 0 (d=%d)", d);
-  HIPPO_REQUIRE(k >= 1 && k <= HIPPO_TOPK_MAX, "hippo_topk_single: k=%d outside 1..%d", k,
-                HIPPO_TOPK_MAX);
-  HIPPO_REQUIRE(row_base >= 0 && row_base + n < 0xffffffffll,
-                "hippo_topk_single: global row numbers must stay below 2^32-1");
-  HIPPO_REQUIRE(q != nullptr && (n == 0 || (bank && norm)), "hippo_topk_single: null pointer");
-  hippo_status st = check_arch();
-  if (st != HIPPO_OK) return st;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int grid = single_grid(n);
-  if (ws == nullptr || ws_bytes < (size_t)grid * k * 8 || ((uintptr_t)ws & 255)) {
-    set_error("hippo_topk_single: workspace of %zu bytes needed (256-byte aligned)",
-              hippo_topk_single_workspace_bytes(n, d, k));
-    return HIPPO_E_WORKSPACE;
-  }
-  uint64_t* part = (uint64_t*)ws;
-  if (n == 0) {
-    HIPPO_CUDA(cudaMemsetAsync(part, 0, (size_t)k * 8, s));
-    return hippo_topk_merge(part, 1, 1, k, k, out_idx, out_score, out_key, stream);
-  }
-  const size_t smem = single_smem_bytes(d, k);
-  HIPPO_REQUIRE(smem <= 200 * 1024, "hippo_topk_single: d=%d too large", d);
-  const __nv_bfloat16* b = (const __nv_bfloat16*)bank;
-  if (d == 1024) {
-    static bool attr4 = false;
-    if (!attr4) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr4 = true; }
-    topk_single_kernel<4><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part);
-  } else {
-    static bool attr0 = false;
-    if (!attr0) { HIPPO_CUDA(cudaFuncSetAttribute(topk_single_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0 = true; }
-    topk_single_kernel<0><<<grid, kSingleThreads, smem, s>>>(b, norm, n, d, q, k, row_base, after_key, part);
-  }
-  HIPPO_CUDA(cudaGetLastError());
-  return hippo_topk_merge(part, grid, 1, k, k, out_idx, out_score, out_key, stream);
+  HIPPO_REQUIRE(world >= 1 && world <= kXchgMaxWorld && rank >= 0 && rank < world, "hippo_topk_single_sharded: bad rank / world");
+  HIPPO_REQUIRE(epoch != 0, "hippo_topk_single_sharded: epoch 0 is the cleared state, start at 1");
+  HIPPO_REQUIRE(world == 1 || peer_bases != nullptr, "hippo_topk_single_sharded: null peer table");
+  HIPPO_REQUIRE(world == 1 || buf_bytes >= hippo_topk_exchange_bytes(world, 1, k),
+                "hippo_topk_single_sharded: symmetric buffer of %zu bytes needed, got %zu",
+                hippo_topk_exchange_bytes(world, 1, k), buf_bytes);
+  SingleTail t{};
+  t.peer_bases = (unsigned char* const*)peer_bases;
+  t.slot_stride = world > 1 ? (buf_bytes - kXchgHeader) / ((size_t)2 * world * sizeof(uint64_t)) : 0;
+  t.rank = rank;
+  t.world = world;
+  t.epoch = epoch;
+  t.out_idx = out_idx;
+  t.out_score = out_score;
+  t.out_key = out_key;
+  return single_launch(bank, norm, n, d, q, k, row_base, after_key, ws, ws_bytes, (cudaStream_t)stream, &t, out_idx,
+                       out_score, out_key, "hippo_topk_single_sharded");
 }
 
 }  // extern "C"

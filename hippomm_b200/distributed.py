@@ -72,6 +72,12 @@ class PeerExchange:
         self.handle.barrier()              # every rank's buffer is cleared before anyone pushes
         self.epoch = 0
 
+    def next_epoch(self) -> int:
+        # 1, 2, ..., 2^32 - 1, then 2, 3, ...: never 0 (the cleared state of the flags), and the parity -- which of
+        # the two gather buffers a call uses -- keeps alternating across the wrap (2^32 - 1 is odd, 2 is even)
+        self.epoch = self.epoch + 1 if self.epoch < 0xFFFFFFFF else 2
+        return self.epoch
+
     def fits(self, nq: int, k: int) -> bool:
         return _lib.load().hippo_topk_exchange_bytes(self.world, nq, k) <= self.nbytes
 
@@ -83,14 +89,46 @@ class PeerExchange:
         idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         score = torch.empty((nq, k), dtype=torch.float32, device=dev)
         key = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        # 1, 2, ..., 2^32 - 1, then 2, 3, ...: never 0 (the cleared state of the flags), and the parity -- which of
-        # the two gather buffers a call uses -- keeps alternating across the wrap (2^32 - 1 is odd, 2 is even)
-        self.epoch = self.epoch + 1 if self.epoch < 0xFFFFFFFF else 2
         with torch.cuda.device(dev):
             _lib.check(lib.hippo_topk_exchange_merge(
                 keys.contiguous().data_ptr(), nq, k_in, k, self.handle.buffer_ptrs_dev, self.nbytes, self.rank,
-                self.world, self.epoch, idx.data_ptr(), score.data_ptr(), key.data_ptr(), _cuda.stream_ptr()))
+                self.world, self.next_epoch(), idx.data_ptr(), score.data_ptr(), key.data_ptr(), _cuda.stream_ptr()))
         return idx, score, key
+
+
+def sharded_search_fused(bank: MemoryBank, queries, k: int, peer: "PeerExchange", path: str = "auto"):
+    """This rank's whole share of a sharded search in ONE C-ABI call: `hippo_topk_batched_sharded` (tcgen05 pass, then
+    one kernel for local merge + NVLink push + global merge) or, for one query, `hippo_topk_single_sharded` (ONE launch:
+    the last CTA of the GEMV merges, pushes, waits and merges).  Returns (idx, score, key) [nq, k], identical on all
+    ranks.  Every rank of the group must make the matching call."""
+    lib = _lib.load()
+    if k > _lib.HIPPO_TOPK_MAX:
+        raise ValueError(f"sharded search supports k <= {_lib.HIPPO_TOPK_MAX}")
+    q = bank._prep_queries(queries)
+    nq = q.shape[0]
+    dev = bank.device
+    if not peer.fits(nq, k):
+        raise ValueError("peer exchange buffers too small for this batch")
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    score = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    key = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    single = path == "single" or (path == "auto" and nq == 1)
+    with torch.cuda.device(dev):
+        stream = _cuda.stream_ptr()
+        if single:
+            ws = _cuda.workspace(lib.hippo_topk_single_workspace_bytes(bank.n, bank.d_pad, k), dev, "topk")
+            for qi in range(nq):
+                _lib.check(lib.hippo_topk_single_sharded(
+                    bank.rows.data_ptr(), bank.norm.data_ptr(), bank.n, bank.d_pad, q[qi].data_ptr(), k, bank.row_base,
+                    None, peer.handle.buffer_ptrs_dev, peer.nbytes, peer.rank, peer.world, peer.next_epoch(),
+                    idx[qi].data_ptr(), score[qi].data_ptr(), key[qi].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        else:
+            ws = _cuda.workspace(lib.hippo_topk_batched_workspace_bytes(bank.n, bank.d_pad, nq, k), dev, "topk")
+            _lib.check(lib.hippo_topk_batched_sharded(
+                bank.rows.data_ptr(), bank.norm.data_ptr(), bank.n, bank.d_pad, q.data_ptr(), nq, k, bank.row_base, None,
+                peer.handle.buffer_ptrs_dev, peer.nbytes, peer.rank, peer.world, peer.next_epoch(),
+                idx.data_ptr(), score.data_ptr(), key.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return idx, score, key
 
 
 class ShardedBank:
@@ -145,6 +183,12 @@ class ShardedBank:
         """Identical (idx, score) on every rank: local top-k, one all-gather, replicated merge."""
         if k > _lib.HIPPO_TOPK_MAX:
             raise ValueError(f"sharded search supports k <= {_lib.HIPPO_TOPK_MAX}")
+        if self.world > 1 and self.exchange != "nccl" and not self._peer_failed:
+            nq = 1 if getattr(queries, "ndim", None) == 1 or (hasattr(queries, "dim") and queries.dim() == 1) else len(queries)
+            peer = self._peer_exchange(nq, k)
+            if peer is not None:
+                idx, score, _ = sharded_search_fused(self.local, queries, k, peer, path)
+                return idx, score
         _, _, keys = self.local.search_keys(queries, k, path)
         if self.world == 1:
             gathered = keys.unsqueeze(0)

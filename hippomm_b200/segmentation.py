@@ -279,6 +279,79 @@ def pattern_separation_batch_device(streams, max_segment_duration: float, min_se
                                                frame_similarity_threshold, audio_silence_threshold, max_segments)
 
 
+def _stream_desc_device(dev, ssim, ft, pcm, pyr, sr, bounds, count, max_segments) -> torch.Tensor:
+    desc = (_lib.StreamDesc * 1)()
+    _fill_stream_desc(desc[0], ssim, ft, pcm, pyr, sr, bounds, count, max_segments)
+    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(desc), ctypes.sizeof(desc)), dtype=np.uint8)
+    staged = torch.empty((raw.size,), dtype=torch.uint8, pin_memory=True)
+    staged.numpy()[:] = raw
+    return staged.to(dev, non_blocking=True)
+
+
+def pattern_separation_device(frames: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],
+                              pcm: Optional[torch.Tensor], sample_rate, max_segment_duration: float,
+                              min_segment_duration: float, frame_similarity_threshold: float,
+                              audio_silence_threshold: float, max_segments: int, chunk_pairs: int = 444):
+    """Temporal pattern separation of ONE stream resident on the device, its stages overlapped.
+
+    The frames are taken in chunks of `chunk_pairs` adjacent pairs (444 = three SSIM CTAs per SM on 148 SMs: one
+    wave).  Chunks alternate between two side streams, so the HBM-bound gray conversion of chunk i + 1 runs under
+    the issue-bound SSIM kernel of chunk i; the audio pyramid runs on a third stream, and so does the boundary
+    state machine in its resumable form: after every chunk it takes the segments whose 30 s window is already
+    covered by finished SSIM values and suspends, so only the last few segments' chain is left when the last chunk
+    is done.  No kernel waits for another kernel (stream events only).  Results are identical to the three
+    stage-by-stage calls.  Returns (bounds fp64 [max_segments, 2], count int32 [1], ssim fp64 [nf - 1] or None)."""
+    lib = _lib.load()
+    ref = frames if frames is not None else pcm
+    dev = _cuda.require_device(ref.device)
+    has_video = frames is not None and frame_times is not None and frames.shape[0] > 0
+    nf = frames.shape[0] if has_video else 0
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        sa, sb, sc = _side_streams(dev, 3)
+        for sd in (sa, sb, sc):
+            sd.wait_stream(main)
+        bounds = torch.empty((max_segments, 2), dtype=torch.float64, device=dev)
+        count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        state = torch.zeros((ctypes.sizeof(_lib.SegmentState),), dtype=torch.uint8, device=dev)
+        ssim = mse = None
+        if nf > 1:
+            ssim = torch.empty((nf - 1,), dtype=torch.float64, device=dev)
+            mse = torch.empty((nf - 1,), dtype=torch.float64, device=dev)
+        pyr = None
+        with torch.cuda.stream(sc):
+            if pcm is not None:
+                pyr = audio_energy_device(pcm)
+            desc = _stream_desc_device(dev, ssim, frame_times if has_video else None, pcm, pyr, sample_rate, bounds,
+                                       count, max_segments)
+        args = (float(max_segment_duration), float(min_segment_duration), float(frame_similarity_threshold),
+                float(audio_silence_threshold))
+        cp = max(1, int(chunk_pairs))
+        starts = list(range(0, nf - 1, cp)) if nf > 1 else []
+        for i, f0 in enumerate(starts):
+            f1 = min(nf - 1, f0 + cp)                      # frames [f0, f1] -> pairs f0 .. f1 - 1
+            sd = (sa, sb)[i & 1]
+            with torch.cuda.stream(sd):
+                frame_pair_scores_device(frames[f0:f1 + 1], range_mode=0, out=(ssim[f0:], mse[f0:]))
+                ev = torch.cuda.Event()
+                ev.record(sd)
+            sc.wait_event(ev)
+            last = i == len(starts) - 1
+            if last or (i & 1):                            # a resume launch after every second chunk, and the final one
+                with torch.cuda.stream(sc):
+                    _lib.check(lib.hippo_segment_boundaries_resume(desc.data_ptr(), 1, state.data_ptr(), f1 + 1,
+                                                                   1 if last else 0, *args, sc.cuda_stream))
+        if not starts:
+            with torch.cuda.stream(sc):
+                _lib.check(lib.hippo_segment_boundaries_resume(desc.data_ptr(), 1, state.data_ptr(), nf, 1, *args,
+                                                               sc.cuda_stream))
+        main.wait_stream(sc)
+        for t in (bounds, count, state, desc, ssim, mse) + (tuple(pyr) if pyr else ()):
+            if t is not None:
+                t.record_stream(main)
+    return bounds, count, ssim
+
+
 def pattern_separation_host(frames, frame_times, pcm, sample_rate, max_segment_duration: float,
                             min_segment_duration: float, frame_similarity_threshold: float,
                             audio_silence_threshold: float, max_segments: int, chunk_frames: int = 384):
@@ -387,7 +460,9 @@ def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio
         raise ValueError("min_segment_duration must be positive (the reference loop would not terminate)")
     dev = _cuda.require_device()
 
-    ssim_d = ft_d = None
+    max_segments = int(math.ceil(total / min_segment_duration)) + 2
+    thresholds = (max_segment_duration, min_segment_duration, frame_similarity_threshold, audio_silence_threshold)
+    ft_d = frames_t = None
     if has_video:
         ft = np.asarray(frame_times, dtype=np.float64)
         if len(video_frames) != len(ft):
@@ -397,23 +472,29 @@ def segment_sequence(video_frames=None, frame_times=None, audio_data=None, audio
         ft_d = _cuda.to_device(ft, dev)
         if len(ft) > 1:
             if isinstance(video_frames, torch.Tensor):
-                frames_d = video_frames.to(dev).contiguous()
+                frames_t = video_frames.contiguous()
             else:
-                frames_d = _cuda.to_device(_load_frames(video_frames), dev)
-            if frames_d.shape[1] < 7 or frames_d.shape[2] < 7:
+                frames_t = torch.from_numpy(_load_frames(video_frames))
+            if frames_t.shape[1] < 7 or frames_t.shape[2] < 7:
                 raise ValueError("win_size exceeds image extent.")
-            ssim_d, _ = frame_pair_scores_device(frames_d, range_mode=0)
-    pcm_d = pyr = None
-    if has_audio:
-        if int(0.5 * audio_sample_rate) < 1:
-            raise ValueError("range() arg 3 must not be zero")                      # hm:1068 with a tiny rate
-        pcm_d = _audio_to_device(audio_data, dev, int16_pcm)
-        pyr = audio_energy_device(pcm_d)
-
-    max_segments = int(math.ceil(total / min_segment_duration)) + 2
-    bounds, count = segment_boundaries_device(
-        ssim_d, ft_d, pcm_d, pyr, audio_sample_rate, max_segment_duration, min_segment_duration,
-        frame_similarity_threshold, audio_silence_threshold, max_segments)
+    if has_audio and int(0.5 * audio_sample_rate) < 1:
+        raise ValueError("range() arg 3 must not be zero")                          # hm:1068 with a tiny rate
+    if frames_t is not None and not frames_t.is_cuda:
+        # host frames: chunked upload on the copy stream, gray + SSIM of chunk i under the upload of chunk i + 1
+        pcm_h = None
+        if has_audio:
+            a = audio_data.detach().cpu() if isinstance(audio_data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(audio_data))
+            if not (a.dtype in (torch.float32, torch.float64) or (int16_pcm and a.dtype == torch.int16)):
+                a = a.to(torch.float64)
+            if a.dim() not in (1, 2):
+                raise ValueError("audio_data must be (n,) or (n, channels)")
+            pcm_h = a.reshape(-1, 1) if a.dim() == 1 else a.contiguous()
+        bounds, count, _ = pattern_separation_host(frames_t, ft_d, pcm_h, audio_sample_rate if has_audio else None,
+                                                   *thresholds, max_segments)
+    else:
+        pcm_d = _audio_to_device(audio_data, dev, int16_pcm) if has_audio else None
+        bounds, count, _ = pattern_separation_device(frames_t, ft_d, pcm_d, audio_sample_rate if has_audio else None,
+                                                     *thresholds, max_segments)
     c = int(count.item())
     if c < 0:
         raise RuntimeError("segment table overflow")

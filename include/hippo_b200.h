@@ -171,6 +171,34 @@ hippo_status hippo_topk_exchange_merge(const uint64_t* local_keys, int32_t nq, i
                                        uint32_t epoch, int64_t* out_idx, float* out_score, uint64_t* out_key,
                                        void* stream);
 
+/*
+ * The sharded searches with NOTHING between the local pass and the exchange: one call = this rank's whole
+ * share of a sharded query (batch).
+ *   hippo_topk_batched_sharded  hippo_topk_batched, but the per-split lists of the tcgen05 pass go straight
+ *                               into the exchange kernel, which merges them per query just before its push
+ *                               phase (local merge + NVLink push + global merge: one launch instead of two).
+ *   hippo_topk_single_sharded   hippo_topk_single, but the LAST CTA of the GEMV to finish (ticket counter)
+ *                               merges the per-block lists, pushes the k keys to every peer, exchanges flags
+ *                               and merges the world x k candidates: a sharded query is ONE launch per rank.
+ * peer_bases / buf_bytes / rank / world / epoch as for hippo_topk_exchange_merge (the same symmetric buffers
+ * and the same epoch sequence serve all three); world == 1 needs no buffers.  Results are identical on every
+ * rank and equal to the single-GPU answer over the whole bank.
+ */
+hippo_status hippo_topk_batched_sharded(const void* bank, const float* norm, int64_t n, int32_t d,
+                                        const float* q, int32_t nq, int32_t k, int64_t row_base,
+                                        const uint64_t* after_key,
+                                        void* const* peer_bases, size_t buf_bytes, int32_t rank,
+                                        int32_t world, uint32_t epoch,
+                                        int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                        void* ws, size_t ws_bytes, void* stream);
+hippo_status hippo_topk_single_sharded(const void* bank, const float* norm, int64_t n, int32_t d,
+                                       const float* q, int32_t k, int64_t row_base,
+                                       const uint64_t* after_key,
+                                       void* const* peer_bases, size_t buf_bytes, int32_t rank,
+                                       int32_t world, uint32_t epoch,
+                                       int64_t* out_idx, float* out_score, uint64_t* out_key,
+                                       void* ws, size_t ws_bytes, void* stream);
+
 /* ---- detailed recall over all events at once ------ */
 /*
  * The reference searches event by event: `for event in long_term_store:

@@ -33,6 +33,16 @@ def main():
             results.setdefault(exchange, []).append((idx.cpu().numpy(), score.cpu().numpy()))
         one, _ = sb.search(q[:1], k)                           # single-query (GEMV) path through the same exchange
         assert np.array_equal(one.cpu().numpy()[0], results[exchange][0][0][0])
+        for qi in (1, 7, 299):                                 # p2p: ONE launch per rank (merge + push + merge in the GEMV's last CTA)
+            oq, sq = sb.search(q[qi], k)
+            assert np.array_equal(oq.cpu().numpy()[0], results[exchange][0][0][qi])
+            assert np.array_equal(sq.cpu().numpy()[0].view(np.uint32), results[exchange][0][1][qi].view(np.uint32))
+        two, _ = sb.search(q[:2], k)                           # two queries: the two-accumulator GEMV behind the batched entry
+        assert np.array_equal(two.cpu().numpy(), results[exchange][0][0][:2])
+        if exchange == "p2p":                                  # the unfused exchange (already merged keys) must agree as well
+            _, _, keys = sb.local.search_keys(q, k, "batched")
+            ui, us, _ = sb._peer.exchange_merge(keys, k)
+            assert np.array_equal(ui.cpu().numpy(), results[exchange][0][0])
     full = MemoryBank.from_rows(rows)
     fi, fs = full.search(q, k, "batched")
     fi, fs = fi.cpu().numpy(), fs.cpu().numpy()

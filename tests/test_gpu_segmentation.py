@@ -273,3 +273,45 @@ def test_audio_scan_near_the_threshold(cuda_device, sr, dtype, nch):
         assert [(s.start_time, s.end_time) for s in segs] == want
         assert len(want) > 3
 
+
+
+@pytest.mark.parametrize("chunk_pairs", [1, 7, 50, 444, 100000])
+def test_overlapped_pipeline_equals_stage_by_stage(cuda_device, chunk_pairs):
+    """pattern_separation_device (frame chunks on alternating streams, audio pyramid and the RESUMABLE boundary chain
+    on a third) and pattern_separation_host (chunked upload from host memory) must return exactly the boundaries of
+    the stage-by-stage calls and of the oracle, whatever the chunking -- including chunks shorter than one 30 s
+    window, where most resume launches find nothing they are allowed to take yet."""
+    from hippomm_b200 import synth
+    from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device, pattern_separation_device,
+                                           pattern_separation_host, segment_boundaries_device)
+
+    nsec, sr = 400, 16000
+    frames, _ = synth.frame_stream(31, nsec, 64, 64, min_scene=5, max_scene=40)
+    pcm = synth.audio_stream_int16(32, nsec * sr)
+    times = np.arange(nsec, dtype=np.float64) * 1.25 + 3.0        # frame_times[0] != 0, non-integer spacing
+    fd = torch.from_numpy(frames).to(cuda_device)
+    pd = torch.from_numpy(pcm.reshape(-1, 1)).to(cuda_device)
+    ft = torch.from_numpy(times).to(cuda_device)
+    ssim, _ = frame_pair_scores_device(fd, range_mode=0)
+    pyr = audio_energy_device(pd)
+    for thr in ((30.0, 10.0, 0.95, -40.0), (10.0, 5.0, 0.95, -40.0)):
+        b0, c0 = segment_boundaries_device(ssim, ft, pd, pyr, sr, *thr, 256)
+        b1, c1, s1 = pattern_separation_device(fd, ft, pd, sr, *thr, 256, chunk_pairs=chunk_pairs)
+        b2, c2, s2 = pattern_separation_host(torch.from_numpy(frames), torch.from_numpy(times), torch.from_numpy(pcm.reshape(-1, 1)),
+                                             sr, *thr, 256, chunk_frames=max(2, min(chunk_pairs, 300)))
+        torch.cuda.synchronize()
+        n = int(c0.item())
+        assert n > 5 and int(c1.item()) == n and int(c2.item()) == n
+        assert torch.equal(b0[:n], b1[:n]) and torch.equal(b0[:n], b2[:n])
+        assert torch.equal(s1, ssim) and torch.equal(s2, ssim)
+    want = O.segment_boundaries(O.adjacent_ssim(frames), list(times), pcm.astype(np.float64).reshape(-1, 1) / 32768.0, sr)
+    b1, c1, _ = pattern_separation_device(fd, ft, pd, sr, 30.0, 10.0, 0.95, -40.0, 256, chunk_pairs=chunk_pairs)
+    n = int(c1.item())
+    assert [tuple(x) for x in b1[:n].cpu().numpy().tolist()] == [tuple(w) for w in want]
+    # audio-only and video-only streams through the same entry
+    ba, ca, _ = pattern_separation_device(None, None, pd, sr, 30.0, 10.0, 0.95, -40.0, 256)
+    wa = O.segment_boundaries(None, None, pcm.astype(np.float64).reshape(-1, 1) / 32768.0, sr)
+    assert [tuple(x) for x in ba[: int(ca.item())].cpu().numpy().tolist()] == [tuple(w) for w in wa]
+    bv, cv, _ = pattern_separation_device(fd, ft, None, None, 30.0, 10.0, 0.95, -40.0, 256, chunk_pairs=chunk_pairs)
+    wv = O.segment_boundaries(O.adjacent_ssim(frames), list(times), None, None)
+    assert [tuple(x) for x in bv[: int(cv.item())].cpu().numpy().tolist()] == [tuple(w) for w in wv]

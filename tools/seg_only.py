@@ -11,6 +11,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device,  # noqa: E402
+                                       pattern_separation_batch_device, pattern_separation_device,
                                        segment_boundaries_device)
 
 device = torch.device("cuda", 0)
@@ -51,6 +52,17 @@ def whole():
 
 
 t_all = timed(whole)
+for cp in [int(x) for x in os.environ.get("CHUNKS", "444").split(",")]:
+    t_ov = timed(lambda: pattern_separation_device(frames, ft, pcm, sr, 30.0, 10.0, 0.95, -40.0, 512, chunk_pairs=cp))
+    o2 = pattern_separation_device(frames, ft, pcm, sr, 30.0, 10.0, 0.95, -40.0, 512, chunk_pairs=cp)
+    torch.cuda.synchronize()
+    same = int(o2[1].item()) == n and torch.equal(o2[0][:n], out[0][:n])
+    print(f"[seg_only] overlapped pipeline, chunks of {cp} pairs: {t_ov:.3f} ms (identical: {same})")
+if os.environ.get("BATCH"):
+    nb = int(os.environ["BATCH"])
+    for lanes in (1, 2, 3):
+        t_b = timed(lambda: pattern_separation_batch_device([(frames, ft, pcm, sr)] * nb, 30.0, 10.0, 0.95, -40.0, 512, lanes=lanes), iters=2, warm=1)
+        print(f"[seg_only] batch of {nb}, {lanes} lanes: {t_b / nb:.3f} ms per stream-hour")
 print(f"[seg_only] segments {n} digest {digest}  frame pairs {t_pairs:.3f} ms  audio pyramid {t_audio:.3f} ms  "
       f"boundaries {t_seg:.3f} ms  whole {t_all:.3f} ms")
 if dbg:
