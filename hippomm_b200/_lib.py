@@ -99,11 +99,15 @@ SIGNATURES = {
     "hippo_consolidate": (_I32, [_P, _I64, _I32, _F32, _F32, _F32, _P, _P, _P, _P, _SZ, _P]),
     "hippo_consolidate_ex_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I64]),
     "hippo_consolidate_ex": (_I32, [_P, _I64, _I32, _F32, _F32, _F32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "hippo_debug_consolidate_timing": (None, [_P]),
     "hippo_frame_pairs_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "hippo_frame_pairs": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _SZ, _P]),
     "hippo_audio_energy": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P]),
     "hippo_audio_levels": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "hippo_segment_boundaries": (_I32, [_P, _I32, _F64, _F64, _F64, _F64, _P]),
+    "hippo_pattern_separation_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
+    "hippo_pattern_separation": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I64, _I32, _F64, _F64, _F64, _F64, _F64,
+                                        _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
     "hippo_segment_boundaries_resume": (_I32, [_P, _I32, _P, _I64, _I32, _F64, _F64, _F64, _F64, _P]),
 }
 

@@ -34,6 +34,7 @@ SOURCES = [
     "frames.cu",
     "audio.cu",
     "segment.cu",
+    "pattern.cu",
 ]
 # per-file extra flags; the boundary state machine must not contract a*b+c into an FMA
 EXTRA_FLAGS = {"segment.cu": ["-fmad=false"]}

@@ -376,6 +376,10 @@ __global__ void iota_kernel(int64_t n, int64_t* out_keep, int32_t* out_count) {
   if (threadIdx.x == 0) *out_count = (int32_t)n;
 }
 
+// HIPPO_CONS_TIMING: CUDA-event time of every launch of the last hippo_consolidate call on this thread, summed per
+// stage {mask (tcgen05), recheck, scan, advance / staging / bank build}; read back with hippo_debug_consolidate_timing
+static thread_local double g_cons_ms[4] = {0, 0, 0, 0};
+
 static int cons_band(int requested = 0) {
   const char* e = getenv("HIPPO_CONS_BAND");
   int b = requested > 0 ? requested : (e ? atoi(e) : kConsBandDefault);
@@ -495,6 +499,17 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
   const int adv_grid = sm_count() * 8;
   const int scan_grid = band / kScanRows + 1;
   const bool dbg_on = getenv("HIPPO_SCAN_DEBUG") != nullptr;
+  const bool timing = getenv("HIPPO_CONS_TIMING") != nullptr;
+  struct Stamp { cudaEvent_t e; int stage; };
+  std::vector<Stamp> stamps;
+  auto stamp = [&](int stage) {           // stage = what ran SINCE the previous stamp
+    if (!timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    stamps.push_back({e, stage});
+  };
+  stamp(3);
   int par = 1;                      // dyn[par] = K before the band being finished
   int64_t prev_r0 = 0;
   int prev_rows = 0;
@@ -507,19 +522,23 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
                                                          par, prev_r0, prev_rows, r0, rows, L.counters + 0, L.unc_cap,
                                                          stats);
     HIPPO_CUDA(cudaGetLastError());
+    stamp(3);
     par ^= 1;                       // dyn[par] = K before this band
     if (rows == 0) break;
     a.dyn_k = dyn + par;
     a.band_rows = rows;
     st = tc_mask_launch(a, s);
     if (st != HIPPO_OK) return st;
+    stamp(0);
     recheck_kernel<<<sm_count() * 4, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
                                                    L.unc_cap, L.mask, L.words_per_row, dyn + par);
     HIPPO_CUDA(cudaGetLastError());
+    stamp(1);
     unsigned long long* dbg = nullptr;
     if (dbg_on) { cudaMalloc(&dbg, (size_t)scan_grid * 64); cudaMemset(dbg, 0, (size_t)scan_grid * 64); }
     greedy_scan_kernel<<<scan_grid, kScanThreads, 0, s>>>(L.mask, L.words_per_row, dyn + par, rows, L.kept[iband & 1], dbg);
     HIPPO_CUDA(cudaGetLastError());
+    stamp(2);
     if (dbg) {
       cudaStreamSynchronize(s);
       std::vector<unsigned long long> h((size_t)scan_grid * 8);
@@ -537,7 +556,22 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
   }
   cons_finish_kernel<<<1, 1, 0, s>>>(dyn, par, L.counters + 2, stats, out_count, out_stats);
   HIPPO_CUDA(cudaGetLastError());
+  if (timing) {
+    stamp(3);
+    cudaStreamSynchronize(s);
+    for (double& v : g_cons_ms) v = 0.0;
+    for (size_t i = 1; i < stamps.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, stamps[i - 1].e, stamps[i].e);
+      g_cons_ms[stamps[i].stage] += ms;
+    }
+    for (auto& x : stamps) cudaEventDestroy(x.e);
+  }
   return HIPPO_OK;
+}
+
+void hippo_debug_consolidate_timing(double* out4_host) {
+  for (int i = 0; i < 4; ++i) out4_host[i] = hippo::g_cons_ms[i];
 }
 
 }  // extern "C"

@@ -137,7 +137,9 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 constexpr int kSsimThreads = 256;
 constexpr int kSsimWarps = kSsimThreads / 32;
 constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
-constexpr int kSsimBand = 112;                 // window rows per band (6 halo rows per band: 5% at 112, 11% at 56)
+constexpr int kSsimBandMin = 14;               // finest band height of a launch (frames_ssim_launch)
+constexpr int kSsimBand = 56;                  // window rows per band (6 halo rows per band: 11%; 112-row bands measured
+                                               // slower on one stream-hour: fewer, longer warp items, longer tail)
 
 // Packed fp32 pairs (sm_100 f32x2 arithmetic): two IEEE round-to-nearest results per instruction.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -161,15 +163,22 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_p
 // One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
 // squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
 // [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
-// three CTAs per SM (at most 80 registers); four at 64 registers measured 3% slower
-__global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_kernel(
-    const uint8_t* __restrict__ gray, int h, int w, int pitch, const int32_t* __restrict__ pair_a,
-    const int32_t* __restrict__ pair_b, const int2* __restrict__ minmax, int range_mode, int bh,
-    int nbands, int nchunks, int64_t nitems, double* __restrict__ part_ssim,
-    unsigned long long* __restrict__ part_sse) {
-  const int lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
-  if (item >= nitems) return;
+struct SsimArgs {
+  const uint8_t* gray; int h, w, pitch;
+  const int32_t* pair_a; const int32_t* pair_b;
+  const int2* minmax; int range_mode, bh, nbands, nchunks;
+  double* part_ssim; unsigned long long* part_sse;   // partials of the launch's items, [nitems]
+};
+
+// One (pair, band, chunk) item, by one warp; `item` numbers the items of ALL pairs (pair-major), `slot` is where its
+// partial sums go.
+__device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64_t slot, int lane) {
+  const uint8_t* __restrict__ gray = A.gray;
+  const int h = A.h, w = A.w, pitch = A.pitch, bh = A.bh, nbands = A.nbands, nchunks = A.nchunks;
+  const int32_t* __restrict__ pair_a = A.pair_a;
+  const int32_t* __restrict__ pair_b = A.pair_b;
+  const int2* __restrict__ minmax = A.minmax;
+  const int range_mode = A.range_mode;
   const int chunk = (int)(item % nchunks);
   const int band = (int)((item / nchunks) % nbands);
   const int p = (int)(item / ((int64_t)nchunks * nbands));
@@ -311,8 +320,36 @@ __global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_kernel(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
   if (lane == 0) {
-    part_ssim[item] = acc;
-    part_sse[item] = sse;
+    A.part_ssim[slot] = acc;
+    A.part_sse[slot] = sse;
+  }
+}
+
+// three CTAs per SM (at most 80 registers); four at 64 registers measured 3% slower
+// Static form: warp i of the grid takes item item0 + i.
+// kCtas = 4 (64 registers, no spill) is 6% faster when the kernel has the machine to itself (hippo_frame_pairs);
+// kCtas = 3 leaves more issue slots to a boundary chain running beside it (pattern.cu), which matters more there.
+template <int kCtas>
+__global__ void __launch_bounds__(kSsimThreads, kCtas) ssim_pair_kernel(const SsimArgs A, int64_t nitems, int64_t item0) {
+  const int64_t i = (int64_t)blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
+  if (i >= nitems) return;
+  ssim_item(A, item0 + i, i, threadIdx.x & 31);
+}
+
+// Persistent form (pattern.cu): every warp keeps taking the next item off a counter until none is left, so the
+// launch ends within one item of its work running out instead of rounding up to whole waves of CTAs, and consecutive
+// launches on different streams hand the SMs over warp by warp.
+// (Tried and dropped: CTAs leaving one SM free for the boundary chain -- with two launches in flight the second
+// launch's CTAs drain through the vacated slots without doing any work.)
+__global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_persistent_kernel(const SsimArgs A, int64_t nitems, int64_t item0,
+                                                                               unsigned int* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if ((int64_t)i >= nitems) break;
+    ssim_item(A, item0 + i, i, lane);
   }
 }
 
@@ -332,7 +369,7 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
 
 struct FrameLayout {
   uint8_t* gray; int2* minmax; double* part_ssim; unsigned long long* part_sse;
-  int pitch, bh, nbands, nchunks, nparts; size_t bytes;
+  int pitch, bh, nbands, nchunks, nparts, nparts_max; size_t bytes;
 };
 static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int npairs) {
   Carver c(ws, ws_bytes);
@@ -345,10 +382,72 @@ static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w,
   L.nbands = out_rows > 0 ? (out_rows + L.bh - 1) / L.bh : 1;
   L.nchunks = out_cols > 0 ? (out_cols + kSsimChunk - 1) / kSsimChunk : 1;
   L.nparts = L.nbands * L.nchunks;
-  L.part_ssim = c.take<double>((size_t)npairs * L.nparts);
-  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts);
+  // room for the finest band height a launch may ask for (kSsimBandMin rows): frames_ssim_launch
+  const int nbands_fine = out_rows > 0 ? (out_rows + kSsimBandMin - 1) / kSsimBandMin : 1;
+  L.nparts_max = nbands_fine * L.nchunks;
+  L.part_ssim = c.take<double>((size_t)npairs * L.nparts_max);
+  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts_max);
   L.bytes = c.used();
   return L;
+}
+
+// ---- the two halves of hippo_frame_pairs for adjacent pairs, separately launchable (pattern.cu): the gray
+// conversion of ALL frames once, then the SSIM of any range of adjacent pairs on any stream ----
+hippo_status frames_gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
+                                cudaStream_t s) {
+  FrameLayout L = frame_layout(ws, ws_bytes, nf, h, w, nf - 1);
+  if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
+    set_error("frames_gray_launch: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
+    return HIPPO_E_WORKSPACE;
+  }
+  HIPPO_REQUIRE(nf <= 65535, "hippo_frame_pairs: at most 65535 frames per call");
+  const int64_t npix = (int64_t)h * w;
+  minmax_init_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.minmax, nf);
+  int bpf = (int)((npix / 16 + 255) / 256);
+  if (bpf < 1) bpf = 1;
+  if (bpf > 64) bpf = 64;
+  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;
+  if (vec) {
+    const int64_t items = (npix / 16 + 31) / 32 * nf;
+    const int64_t want = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
+    gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.minmax);
+  } else {
+    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
+  }
+  HIPPO_CUDA(cudaGetLastError());
+  return HIPPO_OK;
+}
+
+// SSIM (data range from the first frame of each pair, hm:990) + MSE of adjacent pairs [p0, p1) of the nf frames
+// converted by frames_gray_launch into the same workspace.  Persistent warps (see ssim_pair_persistent_kernel);
+// `bh` window rows per band (a multiple of 7 up to kSsimBand: shorter bands = more, shorter items for the chunk that
+// ends the stream); `counter` is a zeroed uint32 nobody else uses (null: one warp per item, static).
+hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes, int p0, int p1, int bh,
+                                unsigned int* counter, double* out_ssim, double* out_mse, cudaStream_t s) {
+  FrameLayout L = frame_layout(ws, ws_bytes, nf, h, w, nf - 1);
+  if (p1 <= p0) return HIPPO_OK;
+  HIPPO_REQUIRE(bh >= 1 && bh <= kSsimBand && kSsimBand % bh == 0, "frames_ssim_launch: band height %d", bh);
+  const int out_rows = h >= 7 ? h - 6 : 0;
+  const int nbands = out_rows > 0 ? (out_rows + bh - 1) / bh : 1;
+  const int nparts = nbands * L.nchunks;          // <= the layout's nparts * (kSsimBand / bh)
+  // the layout reserves nparts(kSsimBand) slots per pair; finer bands need more: frame_layout_fine below sizes for it
+  const int64_t nitems = (int64_t)(p1 - p0) * nparts;
+  const int64_t part_off = (int64_t)p0 * L.nparts_max;
+  const SsimArgs A{L.gray, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, bh, nbands, L.nchunks, L.part_ssim + part_off,
+                   L.part_sse + part_off};
+  int64_t grid = (nitems + kSsimWarps - 1) / kSsimWarps;
+  if (counter != nullptr) {
+    const int64_t cap = (int64_t)sm_count() * 3;
+    if (grid > cap) grid = cap;
+    ssim_pair_persistent_kernel<<<(unsigned)grid, kSsimThreads, 0, s>>>(A, nitems, (int64_t)p0 * nparts, counter);
+  } else {
+    ssim_pair_kernel<3><<<(unsigned)grid, kSsimThreads, 0, s>>>(A, nitems, (int64_t)p0 * nparts);
+  }
+  HIPPO_CUDA(cudaGetLastError());
+  ssim_finalize_kernel<<<(p1 - p0 + 127) / 128, 128, 0, s>>>(L.part_ssim + part_off, L.part_sse + part_off, p1 - p0, nparts, h, w,
+                                                           out_ssim + p0, out_mse ? out_mse + p0 : nullptr);
+  HIPPO_CUDA(cudaGetLastError());
+  return HIPPO_OK;
 }
 
 }  // namespace hippo
@@ -397,9 +496,9 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   HIPPO_CUDA(cudaGetLastError());
   HIPPO_REQUIRE(npairs <= 65535, "hippo_frame_pairs: at most 65535 pairs per call");
   const int64_t nitems = (int64_t)npairs * L.nparts;
-  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(
-      L.gray, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks, nitems, L.part_ssim,
-      L.part_sse);
+  const SsimArgs A{L.gray, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks, L.part_ssim,
+                   L.part_sse};
+  ssim_pair_kernel<4><<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(A, nitems, 0);
   HIPPO_CUDA(cudaGetLastError());
   ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nparts, h, w,
                                                            out_ssim, out_mse);

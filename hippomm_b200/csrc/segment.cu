@@ -341,16 +341,17 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
 static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nstreams, double max_segment_duration,
                                    double min_segment_duration, double frame_similarity_threshold,
                                    double audio_silence_threshold, hippo_segment_state* states, int64_t frames_ready,
-                                   int final_pass, void* stream) {
+                                   int final_pass, void* stream, size_t smem_reserve = 0) {
   using namespace hippo;
   HIPPO_REQUIRE(nstreams >= 0, "hippo_segment_boundaries: nstreams < 0");
   if (nstreams == 0) return HIPPO_OK;
   HIPPO_REQUIRE(streams != nullptr, "hippo_segment_boundaries: null stream table");
   hippo_status st = check_arch();
   if (st != HIPPO_OK) return st;
-  const size_t smem = (size_t)2 * kStageFrames * sizeof(double);
+  size_t smem = (size_t)2 * kStageFrames * sizeof(double);
+  if (smem_reserve > smem) smem = smem_reserve;     // pattern.cu: ask for a whole SM (the extra bytes are never touched)
   static bool attr = false;
-  if (!attr) { HIPPO_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  if (!attr) { HIPPO_CUDA(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
   unsigned long long* dbg = nullptr;
   if (getenv("HIPPO_SEG_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
   segment_kernel<<<nstreams, kSegThreads, smem, (cudaStream_t)stream>>>(
@@ -367,6 +368,15 @@ static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nst
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
+
+namespace hippo {
+hippo_status segment_resume_launch(const hippo_stream_desc* streams, int32_t nstreams, hippo_segment_state* states,
+                                   int64_t frames_ready, int final_pass, double max_dur, double min_dur, double ssim_thr,
+                                   double db_thr, size_t smem_reserve, cudaStream_t s) {
+  return launch_segment(streams, nstreams, max_dur, min_dur, ssim_thr, db_thr, states, frames_ready, final_pass, (void*)s,
+                        smem_reserve);
+}
+}  // namespace hippo
 
 extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t nstreams,
                                                  double max_segment_duration, double min_segment_duration,

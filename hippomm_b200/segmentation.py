@@ -242,113 +242,125 @@ def segment_boundaries_batch_device(streams, max_segment_duration: float, min_se
 
 def pattern_separation_batch_device(streams, max_segment_duration: float, min_segment_duration: float,
                                     frame_similarity_threshold: float, audio_silence_threshold: float,
-                                    max_segments: int, lanes: int = 2):
+                                    max_segments: int, lanes: int = 2, mode: str = "stages"):
     """Temporal pattern separation of several independent streams resident on the device.
 
     `streams`: list of (frames uint8 [nf, h, w, ch] or None, frame_times fp64 [nf] or None, pcm [ns, nch] or None,
-    sample_rate).  The per-stream kernels (gray + SSIM, audio pyramid) of consecutive streams are issued on `lanes`
-    alternating CUDA streams, so the HBM-bound gray conversion of one stream overlaps the issue-bound SSIM kernel of
-    another; ONE boundary launch (one CTA per stream) follows on the caller's stream.  Scratch is per CUDA stream
-    (`_cuda.workspace`), results are the same as stream-by-stream calls.
+    sample_rate).
+    mode "stages" (default, the faster one for a batch): the per-stream kernels (gray + SSIM, audio pyramid) of
+      consecutive streams are issued on `lanes` alternating CUDA streams, so the HBM-bound gray conversion of one
+      stream overlaps the issue-bound SSIM kernel of another; ONE boundary launch (one CTA per stream: the sequential
+      chains of all streams side by side) follows on the caller's stream.
+    mode "pipeline": every stream goes through `pattern_separation_device` (its own stages overlapped), consecutive
+      streams issued from `lanes` alternating CUDA streams.
+    Scratch is per CUDA stream (`_cuda.workspace`); results are the same as stream-by-stream calls.
     Returns (bounds fp64 [n, max_segments, 2], counts int32 [n])."""
     if not streams:
         raise ValueError("no streams")
+    if mode not in ("stages", "pipeline"):
+        raise ValueError(f"unknown mode {mode!r}")
     ref = next(t for st in streams for t in (st[0], st[2]) if t is not None)
     dev = _cuda.require_device(ref.device)
+    n = len(streams)
+    lanes = max(1, int(lanes))
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
-        side = _side_streams(dev, max(1, int(lanes)))
-        for sd in side:
+        if mode == "stages":
+            side = _side_streams(dev, lanes)
+            for sd in side:
+                sd.wait_stream(main)
+            prepared = []
+            for i, (frames, ft, pcm, sr) in enumerate(streams):
+                sd = side[i % len(side)]
+                with torch.cuda.stream(sd):
+                    ssim = pyr = None
+                    if frames is not None and frames.shape[0] > 1:
+                        ssim, _ = frame_pair_scores_device(frames, range_mode=0)
+                        ssim.record_stream(main)
+                    if pcm is not None:
+                        pyr = audio_energy_device(pcm)
+                        pyr[0].record_stream(main)
+                        pyr[1].record_stream(main)
+                prepared.append((ssim, ft, pcm, pyr, sr))
+            for sd in side:
+                main.wait_stream(sd)
+            return segment_boundaries_batch_device(prepared, max_segment_duration, min_segment_duration,
+                                                   frame_similarity_threshold, audio_silence_threshold, max_segments)
+        bounds = torch.empty((n, max_segments, 2), dtype=torch.float64, device=dev)
+        counts = torch.zeros((n,), dtype=torch.int32, device=dev)
+        issue = _issue_streams(dev, lanes)
+        for sd in issue:
             sd.wait_stream(main)
-        prepared = []
         for i, (frames, ft, pcm, sr) in enumerate(streams):
-            sd = side[i % len(side)]
-            with torch.cuda.stream(sd):
-                ssim = pyr = None
-                if frames is not None and frames.shape[0] > 1:
-                    ssim, _ = frame_pair_scores_device(frames, range_mode=0)
-                    ssim.record_stream(main)
-                if pcm is not None:
-                    pyr = audio_energy_device(pcm)
-                    pyr[0].record_stream(main)
-                    pyr[1].record_stream(main)
-            prepared.append((ssim, ft, pcm, pyr, sr))
-        for sd in side:
+            slot = i % lanes
+            with torch.cuda.stream(issue[slot]):
+                b, c, _ = pattern_separation_device(frames, ft, pcm, sr, max_segment_duration, min_segment_duration,
+                                                    frame_similarity_threshold, audio_silence_threshold, max_segments,
+                                                    slot=slot)
+                bounds[i].copy_(b, non_blocking=True)
+                counts[i:i + 1].copy_(c, non_blocking=True)
+        for sd in issue:
             main.wait_stream(sd)
-        return segment_boundaries_batch_device(prepared, max_segment_duration, min_segment_duration,
-                                               frame_similarity_threshold, audio_silence_threshold, max_segments)
-
-
-def _stream_desc_device(dev, ssim, ft, pcm, pyr, sr, bounds, count, max_segments) -> torch.Tensor:
-    desc = (_lib.StreamDesc * 1)()
-    _fill_stream_desc(desc[0], ssim, ft, pcm, pyr, sr, bounds, count, max_segments)
-    raw = np.frombuffer(ctypes.string_at(ctypes.addressof(desc), ctypes.sizeof(desc)), dtype=np.uint8)
-    staged = torch.empty((raw.size,), dtype=torch.uint8, pin_memory=True)
-    staged.numpy()[:] = raw
-    return staged.to(dev, non_blocking=True)
+            bounds.record_stream(sd)
+            counts.record_stream(sd)
+    return bounds, counts
 
 
 def pattern_separation_device(frames: Optional[torch.Tensor], frame_times: Optional[torch.Tensor],
                               pcm: Optional[torch.Tensor], sample_rate, max_segment_duration: float,
                               min_segment_duration: float, frame_similarity_threshold: float,
-                              audio_silence_threshold: float, max_segments: int, chunk_pairs: int = 444):
-    """Temporal pattern separation of ONE stream resident on the device, its stages overlapped.
+                              audio_silence_threshold: float, max_segments: int, chunk_pairs: int = 444,
+                              slot: int = 0):
+    """Temporal pattern separation of ONE stream resident on the device, its stages overlapped
+    (`hippo_pattern_separation`: ONE C-ABI call issues every launch).
 
     The frames are taken in chunks of `chunk_pairs` adjacent pairs (444 = three SSIM CTAs per SM on 148 SMs: one
     wave).  Chunks alternate between two side streams, so the HBM-bound gray conversion of chunk i + 1 runs under
     the issue-bound SSIM kernel of chunk i; the audio pyramid runs on a third stream, and so does the boundary
-    state machine in its resumable form: after every chunk it takes the segments whose 30 s window is already
-    covered by finished SSIM values and suspends, so only the last few segments' chain is left when the last chunk
-    is done.  No kernel waits for another kernel (stream events only).  Results are identical to the three
-    stage-by-stage calls.  Returns (bounds fp64 [max_segments, 2], count int32 [1], ssim fp64 [nf - 1] or None)."""
+    state machine in its resumable form: after every second chunk it takes the segments whose 30 s window is
+    already covered by finished SSIM values and suspends, so only the last few segments' chain is left when the
+    last chunk is done.  No kernel waits for another kernel (stream events only).  Results are identical to the
+    three stage-by-stage calls.  `slot` picks one of several independent sets of side streams / scratch, so that
+    calls for different streams issued from different CUDA streams can overlap each other.
+    Returns (bounds fp64 [max_segments, 2], count int32 [1], ssim fp64 [nf - 1] or None)."""
     lib = _lib.load()
     ref = frames if frames is not None else pcm
     dev = _cuda.require_device(ref.device)
     has_video = frames is not None and frame_times is not None and frames.shape[0] > 0
-    nf = frames.shape[0] if has_video else 0
+    if has_video and (frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_contiguous()):
+        raise ValueError("frames must be a contiguous uint8 [n, h, w, ch] tensor")
+    nf, h, w, ch = (frames.shape if has_video else (0, 1, 1, 1))
     with torch.cuda.device(dev):
-        main = torch.cuda.current_stream()
-        sa, sb, sc = _side_streams(dev, 3)
-        for sd in (sa, sb, sc):
-            sd.wait_stream(main)
+        side = _side_streams(dev, 3 * (slot + 1))[3 * slot: 3 * slot + 3]
         bounds = torch.empty((max_segments, 2), dtype=torch.float64, device=dev)
         count = torch.zeros((1,), dtype=torch.int32, device=dev)
-        state = torch.zeros((ctypes.sizeof(_lib.SegmentState),), dtype=torch.uint8, device=dev)
-        ssim = mse = None
+        ssim = mse = e16 = e512 = None
         if nf > 1:
             ssim = torch.empty((nf - 1,), dtype=torch.float64, device=dev)
             mse = torch.empty((nf - 1,), dtype=torch.float64, device=dev)
-        pyr = None
-        with torch.cuda.stream(sc):
-            if pcm is not None:
-                pyr = audio_energy_device(pcm)
-            desc = _stream_desc_device(dev, ssim, frame_times if has_video else None, pcm, pyr, sample_rate, bounds,
-                                       count, max_segments)
-        args = (float(max_segment_duration), float(min_segment_duration), float(frame_similarity_threshold),
-                float(audio_silence_threshold))
-        cp = max(1, int(chunk_pairs))
-        starts = list(range(0, nf - 1, cp)) if nf > 1 else []
-        for i, f0 in enumerate(starts):
-            f1 = min(nf - 1, f0 + cp)                      # frames [f0, f1] -> pairs f0 .. f1 - 1
-            sd = (sa, sb)[i & 1]
-            with torch.cuda.stream(sd):
-                frame_pair_scores_device(frames[f0:f1 + 1], range_mode=0, out=(ssim[f0:], mse[f0:]))
-                ev = torch.cuda.Event()
-                ev.record(sd)
-            sc.wait_event(ev)
-            last = i == len(starts) - 1
-            if last or (i & 1):                            # a resume launch after every second chunk, and the final one
-                with torch.cuda.stream(sc):
-                    _lib.check(lib.hippo_segment_boundaries_resume(desc.data_ptr(), 1, state.data_ptr(), f1 + 1,
-                                                                   1 if last else 0, *args, sc.cuda_stream))
-        if not starts:
-            with torch.cuda.stream(sc):
-                _lib.check(lib.hippo_segment_boundaries_resume(desc.data_ptr(), 1, state.data_ptr(), nf, 1, *args,
-                                                               sc.cuda_stream))
-        main.wait_stream(sc)
-        for t in (bounds, count, state, desc, ssim, mse) + (tuple(pyr) if pyr else ()):
-            if t is not None:
-                t.record_stream(main)
+        ns = nch = 0
+        if pcm is not None:
+            if pcm.dim() == 1:
+                pcm = pcm.reshape(-1, 1)
+            ns, nch = pcm.shape
+            # the pyramid is scratch of this call: grow-only buffer per (slot, stream), not a fresh 29 MB block per call
+            n16, n512 = max((ns + 15) // 16, 1), max((ns + 511) // 512, 1)
+            pyr = _cuda.workspace((n16 + n512) * 8, dev, f"pattern_pyr{slot}").view(torch.float64)
+            e16, e512 = pyr[:n16], pyr[n16:n16 + n512]
+        ft = frame_times.to(dev, torch.float64).contiguous() if has_video else None
+        ws = _cuda.workspace(lib.hippo_pattern_separation_workspace_bytes(nf, h, w, int(chunk_pairs)), dev, f"pattern{slot}")
+        sides = (ctypes.c_void_p * 3)(*[s.cuda_stream for s in side])
+        # every buffer was allocated on the caller's stream, the side streams start behind an event recorded on it
+        # after that, and it is joined behind them before the call returns: to the caching allocator this is plain
+        # single-stream use (record_stream on the side streams would only force a fresh cudaMalloc per call)
+        _lib.check(lib.hippo_pattern_separation(
+            _cuda.ptr(frames) if has_video else None, nf, h, w, ch, _cuda.ptr(ft),
+            _cuda.ptr(pcm), _PCM_ENUM[pcm.dtype] if pcm is not None else _lib.HIPPO_F64, ns, max(nch, 1),
+            float(sample_rate) if (pcm is not None and sample_rate) else 0.0,
+            float(max_segment_duration), float(min_segment_duration), float(frame_similarity_threshold),
+            float(audio_silence_threshold), int(chunk_pairs), _cuda.ptr(ssim), _cuda.ptr(mse), _cuda.ptr(e16),
+            _cuda.ptr(e512), bounds.data_ptr(), count.data_ptr(), int(max_segments), ws.data_ptr(), ws.numel(),
+            sides, _cuda.stream_ptr()))
     return bounds, count, ssim
 
 
@@ -414,6 +426,14 @@ def pattern_separation_host(frames, frame_times, pcm, sample_rate, max_segment_d
 
 
 _side: dict = {}
+_issue: dict = {}
+
+
+def _issue_streams(dev: torch.device, n: int):
+    pool = _issue.setdefault(dev.index, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def _side_streams(dev: torch.device, n: int):

@@ -280,6 +280,14 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
                                   int64_t* out_keep, int32_t* out_count, int32_t* out_stats,
                                   void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * Profiling aid (never needed in production): when the environment variable HIPPO_CONS_TIMING is set,
+ * hippo_consolidate[_ex] brackets every launch with CUDA events, synchronises at the end and keeps the
+ * time per stage of the LAST call on the calling thread; this returns them in milliseconds (HOST array):
+ * {similarity bits on tcgen05, fp32 re-evaluation, greedy scan, bank build + band staging / compaction}.
+ */
+void         hippo_debug_consolidate_timing(double* out4_host);
+
 /* ---- temporal pattern separation ---------------------------------------- */
 /*
  * Frame-pair scoring: BGR -> gray (cv2's fixed-point BGR2GRAY) -> mean SSIM
@@ -376,6 +384,31 @@ hippo_status hippo_segment_boundaries_resume(const hippo_stream_desc* streams, i
                                              double max_segment_duration, double min_segment_duration,
                                              double frame_similarity_threshold,
                                              double audio_silence_threshold, void* stream);
+
+/*
+ * One stream, all stages, overlapped (hm:1002-1114 with hm:980-1000 underneath): the frames are taken in
+ * chunks of `chunk_pairs` adjacent pairs (0 = 444) whose gray conversion + SSIM alternate between
+ * side_streams_host[0] and [1]; the audio pyramid and the resumable boundary state machine run on
+ * side_streams_host[2], the chain advancing after every second chunk.  `stream` is joined at both ends
+ * (events), so the call behaves like any other asynchronous call on `stream`.  The results equal
+ * hippo_frame_pairs + hippo_audio_energy + hippo_segment_boundaries run one after the other.
+ *   frames / frame_times  NULL = no video;  pcm NULL = no audio (then out_e16 / out_e512 may be NULL)
+ *   out_ssim, out_mse     [nf - 1] fp64;  out_e16 [ceil(ns/16)], out_e512 [ceil(ns/512)] fp64
+ *   side_streams_host     HOST array of three cudaStream_t distinct from `stream` and from each other
+ * The events used for the ordering are created once per host thread and kept (the only allocation
+ * any entry point of this library performs).
+ */
+size_t       hippo_pattern_separation_workspace_bytes(int32_t nf, int32_t h, int32_t w, int32_t chunk_pairs);
+hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t h, int32_t w, int32_t ch,
+                                      const double* frame_times,
+                                      const void* pcm, int32_t pcm_dtype, int64_t ns, int32_t nch,
+                                      double sample_rate,
+                                      double max_segment_duration, double min_segment_duration,
+                                      double frame_similarity_threshold, double audio_silence_threshold,
+                                      int32_t chunk_pairs,
+                                      double* out_ssim, double* out_mse, double* out_e16, double* out_e512,
+                                      double* out_bounds, int32_t* out_count, int32_t max_segments,
+                                      void* ws, size_t ws_bytes, void* const* side_streams_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -232,12 +232,12 @@ def test_pattern_separation_batch_on_alternating_cuda_streams(cuda_device, lanes
         b1, c1 = segment_boundaries_device(ssim, ft, pcm, pyr, sr if audio else None, 30.0, 10.0, 0.95, -40.0, 64)
         torch.cuda.synchronize()
         want.append(b1[: int(c1.item())].clone())
-    for _ in range(2):
-        bounds, counts = pattern_separation_batch_device(inputs, 30.0, 10.0, 0.95, -40.0, 64, lanes=lanes)
+    for mode in ("stages", "pipeline", "stages", "pipeline"):
+        bounds, counts = pattern_separation_batch_device(inputs, 30.0, 10.0, 0.95, -40.0, 64, lanes=lanes, mode=mode)
         torch.cuda.synchronize()
         for i, w in enumerate(want):
-            assert int(counts[i].item()) == len(w) > 0
-            assert torch.equal(bounds[i, : len(w)], w)
+            assert int(counts[i].item()) == len(w) > 0, mode
+            assert torch.equal(bounds[i, : len(w)], w), mode
 
 
 @pytest.mark.parametrize("sr,dtype,nch", [(16000, "i16", 1), (8000, "i16", 1), (22050, "f32", 1), (44100, "i16", 2),

@@ -58,11 +58,22 @@ for cp in [int(x) for x in os.environ.get("CHUNKS", "444").split(",")]:
     torch.cuda.synchronize()
     same = int(o2[1].item()) == n and torch.equal(o2[0][:n], out[0][:n])
     print(f"[seg_only] overlapped pipeline, chunks of {cp} pairs: {t_ov:.3f} ms (identical: {same})")
+if os.environ.get("TAIL"):
+    for nfr in (3553, 3600, 3109, 2665):
+        sub = frames[:nfr].contiguous()
+        t = timed(lambda: frame_pair_scores_device(sub, range_mode=0))
+        print(f"[seg_only] frame pairs on {nfr} frames: {t:.3f} ms")
+if os.environ.get("TIMELINE"):
+    os.environ["HIPPO_PATTERN_DEBUG"] = "1"
+    pattern_separation_device(frames, ft, pcm, sr, 30.0, 10.0, 0.95, -40.0, 512, chunk_pairs=int(os.environ["TIMELINE"]))
+    torch.cuda.synchronize()
+    del os.environ["HIPPO_PATTERN_DEBUG"]
 if os.environ.get("BATCH"):
     nb = int(os.environ["BATCH"])
-    for lanes in (1, 2, 3):
-        t_b = timed(lambda: pattern_separation_batch_device([(frames, ft, pcm, sr)] * nb, 30.0, 10.0, 0.95, -40.0, 512, lanes=lanes), iters=2, warm=1)
-        print(f"[seg_only] batch of {nb}, {lanes} lanes: {t_b / nb:.3f} ms per stream-hour")
+    for mode in ("stages", "pipeline"):
+        for lanes in (1, 2, 3):
+            t_b = timed(lambda: pattern_separation_batch_device([(frames, ft, pcm, sr)] * nb, 30.0, 10.0, 0.95, -40.0, 512, lanes=lanes, mode=mode), iters=2, warm=1)
+            print(f"[seg_only] batch of {nb}, {mode}, {lanes} lanes: {t_b / nb:.3f} ms per stream-hour")
 print(f"[seg_only] segments {n} digest {digest}  frame pairs {t_pairs:.3f} ms  audio pyramid {t_audio:.3f} ms  "
       f"boundaries {t_seg:.3f} ms  whole {t_all:.3f} ms")
 if dbg:
