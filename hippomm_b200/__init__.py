@@ -63,7 +63,7 @@ def _m_segment_sequence(self, video_frames=None, frame_times=None, audio_data=No
                     frame_times=s.frame_times) for s in segs]
 
 
-def install(cache_banks: bool = False) -> None:
+def install(cache_banks: bool = False, event_store: bool = False) -> None:
     """Rebind the reference's hot-path symbols to the GPU implementations:
 
       hippomm.utils.vector_ops.{top_k_cosine_similarity, cosine_similarity}
@@ -75,6 +75,12 @@ def install(cache_banks: bool = False) -> None:
     skipped; at least vector_ops must succeed.  cache_banks=True keeps device banks of recently searched
     feature arrays that are READ-ONLY (`arr.flags.writeable = False`; keyed by object identity) so repeated
     queries skip the upload; writeable arrays are searched straight from the upload on every call.
+
+    event_store=True additionally hooks the ThetaEvent store (hippomm_b200/store.py): `save_theta_event` /
+    `load_theta_event` (hm:320-449) write / prefer a binary sidecar next to each event's JSON file (same return type,
+    no decimal-text parsing on reload), and `QARecallSystem._find_relevant_{video,audio}_segments` (hm:3127-3383) search
+    ONE cross-event device bank per modality with `hippo_topk_segmented` + `hippo_recall_windows` instead of looping
+    over the events; events that would take the reference's LLM branch hand the call back to the reference's method.
     """
     import importlib
 
@@ -99,6 +105,12 @@ def install(cache_banks: bool = False) -> None:
         H._segment_sequence = _m_segment_sequence
         H._compute_frame_similarity = _m_compute_frame_similarity
         H._compute_audio_level = _m_compute_audio_level
+        if event_store and "store" not in _saved:
+            from . import store
+
+            store.install_event_store(hm, _saved)
+    elif event_store:
+        raise ImportError("install(event_store=True) needs hippomm.core.hippocampal_memory to be importable")
     try:
         bp = importlib.import_module("hippomm.core.batch_process")
     except Exception:
@@ -110,6 +122,10 @@ def install(cache_banks: bool = False) -> None:
 
 def uninstall() -> None:
     """Undo install()."""
+    if "store" in _saved:
+        from . import store
+
+        store.uninstall_event_store(_saved)
     if "vo" in _saved:
         vo, f1, f2 = _saved.pop("vo")
         vo.top_k_cosine_similarity, vo.cosine_similarity = f1, f2

@@ -83,7 +83,7 @@ SIGNATURES = {
     "hippo_topk_batched": (_I32, [_P, _P, _I64, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "hippo_topk_rows_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "hippo_topk_rows": (_I32, [_P, _I32, _I64, _I32, _I64, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
-    "hippo_rescore": (_I32, [_P, _I32, _I64, _I32, _I64, _I64, _P, _I32, _I32, _P, _I32, _P, _P, _P]),
+    "hippo_rescore": (_I32, [_P, _I32, _I64, _I32, _I64, _I64, _P, _I32, _I64, _I32, _P, _I32, _P, _P, _P]),
     "hippo_topk_merge": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hippo_topk_exchange_bytes": (_SZ, [_I32, _I32, _I32]),
     "hippo_topk_exchange_merge": (_I32, [_P, _I32, _I32, _I32, _P, _SZ, _I32, _I32, C.c_uint32, _P, _P, _P, _P]),

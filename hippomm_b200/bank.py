@@ -90,7 +90,7 @@ def search_rows(rows: torch.Tensor, query: torch.Tensor, k: int, row_base: int =
                 cursor = key[done - 1:done].clone()
         score = torch.empty((k,), dtype=torch.float64, device=dev)
         _lib.check(lib.hippo_rescore(rows.data_ptr(), _T2ENUM[rows.dtype], n, d, rows.stride(0), row_base, q.data_ptr(),
-                                     _T2ENUM[q.dtype], 1, idx.data_ptr(), k, None, score.data_ptr(), stream))
+                                     _T2ENUM[q.dtype], d, 1, idx.data_ptr(), k, None, score.data_ptr(), stream))
     return idx, score
 
 
@@ -355,7 +355,8 @@ class MemoryBank:
                 r_key = torch.empty((nq, kmax), dtype=torch.int64, device=dev)
                 _lib.check(lib.hippo_rescore(
                     self.src.data_ptr(), _T2ENUM[self.src.dtype], self.n, self.d, self.src.stride(0), self.row_base,
-                    q_src.data_ptr(), _lib.HIPPO_F32, nq, p_idx.data_ptr(), kmax, r_key.data_ptr(), None, stream))
+                    q_src.data_ptr(), _lib.HIPPO_F32, q_src.stride(0), nq, p_idx.data_ptr(), kmax, r_key.data_ptr(), None,
+                    stream))
                 pages_keys.append(r_key)
                 allk = torch.stack(pages_keys).contiguous()
                 idx = torch.empty((nq, k), dtype=torch.int64, device=dev)

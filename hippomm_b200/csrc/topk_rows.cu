@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(kRowsThreads) topk_rows_kernel(
 // One warp per (query, candidate): exact cosine of candidate row cand[qi][j] with query qi.
 template <typename T, typename Q>
 __global__ void __launch_bounds__(kRowsThreads) rescore_kernel(
-    const T* __restrict__ rows, int64_t n, int d, int64_t ld, int64_t row_base, const Q* __restrict__ q, int nq,
-    const int64_t* __restrict__ cand, int kc, uint64_t* __restrict__ out_key, double* __restrict__ out_score) {
+    const T* __restrict__ rows, int64_t n, int d, int64_t ld, int64_t row_base, const Q* __restrict__ q, int64_t q_ld,
+    int nq, const int64_t* __restrict__ cand, int kc, uint64_t* __restrict__ out_key, double* __restrict__ out_score) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
   if (w >= (int64_t)nq * kc) return;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kRowsThreads) rescore_kernel(
     return;
   }
   const T* row = rows + r * ld;
-  const Q* qv = q + (size_t)qi * d;
+  const Q* qv = q + (size_t)qi * q_ld;
   double a = 0.0, s = 0.0, t = 0.0;
   for (int c = lane; c < d; c += 32) {
     const double x = (double)row[c], y = (double)qv[c];
@@ -232,10 +232,10 @@ hippo_status hippo_topk_rows(const void* rows, int32_t dtype, int64_t n, int32_t
 }
 
 hippo_status hippo_rescore(const void* rows, int32_t dtype, int64_t n, int32_t d, int64_t ld, int64_t row_base,
-                           const void* q, int32_t q_dtype, int32_t nq, const int64_t* cand_idx, int32_t kc,
-                           uint64_t* out_key, double* out_score, void* stream) {
+                           const void* q, int32_t q_dtype, int64_t q_ld, int32_t nq, const int64_t* cand_idx,
+                           int32_t kc, uint64_t* out_key, double* out_score, void* stream) {
   using namespace hippo;
-  HIPPO_REQUIRE(n >= 0 && d > 0 && ld >= d && nq >= 0 && kc >= 1, "hippo_rescore: bad sizes");
+  HIPPO_REQUIRE(n >= 0 && d > 0 && ld >= d && nq >= 0 && kc >= 1 && (q_ld == 0 || q_ld >= d), "hippo_rescore: bad sizes");
   HIPPO_REQUIRE((dtype == HIPPO_F32 || dtype == HIPPO_F64) && (q_dtype == HIPPO_F32 || q_dtype == HIPPO_F64),
                 "hippo_rescore: rows and queries must be fp32 or fp64");
   if (nq == 0) return HIPPO_OK;
@@ -246,8 +246,8 @@ hippo_status hippo_rescore(const void* rows, int32_t dtype, int64_t n, int32_t d
   const int64_t warps = (int64_t)nq * kc;
   const unsigned grid = (unsigned)((warps + kRowsWarps - 1) / kRowsWarps);
 #define HIPPO_RESCORE_LAUNCH(T, Q)                                                                                \
-  rescore_kernel<T, Q><<<grid, kRowsThreads, 0, s>>>((const T*)rows, n, d, ld, row_base, (const Q*)q, nq, cand_idx, \
-                                                     kc, out_key, out_score)
+  rescore_kernel<T, Q><<<grid, kRowsThreads, 0, s>>>((const T*)rows, n, d, ld, row_base, (const Q*)q, q_ld, nq, \
+                                                     cand_idx, kc, out_key, out_score)
   if (dtype == HIPPO_F32 && q_dtype == HIPPO_F32) HIPPO_RESCORE_LAUNCH(float, float);
   else if (dtype == HIPPO_F32) HIPPO_RESCORE_LAUNCH(float, double);
   else if (q_dtype == HIPPO_F32) HIPPO_RESCORE_LAUNCH(double, float);

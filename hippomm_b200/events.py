@@ -78,9 +78,11 @@ class EventBank:
 
     # ------------------------------------------------------------------ build ----
     @classmethod
-    def from_events(cls, events, modality: str = "vision", device=None) -> "EventBank":
+    def from_events(cls, events, modality: str = "vision", device=None, keep_rows: bool = False) -> "EventBank":
         """Events are the reference's ThetaEvent objects (or dicts with the same fields); those without
-        `modality` in their features are skipped, as hm:3144-3145 / hm:3296-3297 skip them."""
+        `modality` in their features are skipped, as hm:3144-3145 / hm:3296-3297 skip them.
+        keep_rows=True also keeps the rows in their own precision (fp32, or the fp64 of a store reloaded from JSON,
+        hm:391) on the device: `search(..., exact=True)` re-scores its bf16 candidates from them."""
         rows, times, index = [], [], []
         for i, ev in enumerate(events):
             f = _event_rows(ev, modality)
@@ -99,7 +101,9 @@ class EventBank:
         offsets[1:] = np.cumsum([len(f) for f in rows])
         toffsets = np.zeros(len(rows) + 1, dtype=np.int64)
         toffsets[1:] = np.cumsum([len(t) for t in times])
-        bank = MemoryBank(int(offsets[-1]), d, device=device)
+        wide = any(f.dtype == np.float64 for f in rows)
+        bank = MemoryBank(int(offsets[-1]), d, device=device, keep_rows=keep_rows,
+                          rows_dtype=torch.float64 if wide else torch.float32)
         for f, o in zip(rows, offsets[:-1]):
             if len(f):
                 bank.fill(int(o), f if f.dtype in (np.float32, np.float64) else f.astype(np.float32))
@@ -130,11 +134,18 @@ class EventBank:
                                                out.data_ptr(), _cuda.stream_ptr()))
         return out[: b.n]
 
-    def search(self, query, k: int = 5):
+    def search(self, query, k: int = 5, exact: bool = False):
         """Every event's top-k in one pass: (idx int64 [nev, k] event-local rows, -1 padded;
-        score fp32 [nev, k]; maxsim fp32 [nev]) as device tensors."""
+        score fp32 [nev, k]; maxsim fp32 [nev]) as device tensors.
+        exact=True (bank built with keep_rows): the bf16 pass nominates HIPPO_TOPK_MAX candidates per event, every
+        candidate is re-scored from the original rows (`hippo_rescore`) and re-ranked; an event whose k-th exact score
+        does not clear `last bf16 candidate + eps` (a rigorous bound on the bf16 error, see bank.py) is searched again
+        straight from its original rows (`hippo_topk_rows`).  Rows and order then equal the reference's wherever its
+        own scores differ by more than rounding noise."""
         if k < 1:
             raise ValueError("k must be >= 1")
+        if exact:
+            return self._search_exact(query, k)
         lib = _lib.load()
         q = self._query(query)
         b = self.bank
@@ -151,6 +162,47 @@ class EventBank:
                     self.nev, k, idx.data_ptr(), score.data_ptr(), mx.data_ptr(), ws.data_ptr(), ws.numel(),
                     _cuda.stream_ptr()))
         return idx, score, mx[: self.nev]
+
+    def _search_exact(self, query, k: int):
+        from .bank import _EPS_BF16, _T2ENUM, search_rows
+
+        b = self.bank
+        if b.src is None:
+            raise ValueError("exact search needs the original rows: build the EventBank with keep_rows=True")
+        lib = _lib.load()
+        dev = b.device
+        kc = _lib.HIPPO_TOPK_MAX
+        if k > kc:
+            raise ValueError(f"exact per-event search supports k <= {kc}")
+        c_idx, c_score, _ = self.search(query, kc)                  # bf16 candidates, event-local rows
+        q = self._query(query)[: b.d].contiguous()
+        nev = self.nev
+        glob = torch.where(c_idx >= 0, c_idx + self._offsets_d[:nev, None], c_idx).contiguous()
+        r_key = torch.empty((nev, kc), dtype=torch.int64, device=dev)
+        idx = torch.empty((nev, k), dtype=torch.int64, device=dev)
+        score = torch.empty((nev, k), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _cuda.stream_ptr()
+            _lib.check(lib.hippo_rescore(b.src.data_ptr(), _T2ENUM[b.src.dtype], b.n, b.d, b.src.stride(0), 0, q.data_ptr(),
+                                         _lib.HIPPO_F32, 0, nev, glob.data_ptr(), kc, r_key.data_ptr(), None, stream))
+            _lib.check(lib.hippo_topk_merge(r_key.data_ptr(), 1, nev, kc, k, idx.data_ptr(), score.data_ptr(), None, stream))
+        idx = torch.where(idx >= 0, idx - self._offsets_d[:nev, None], idx)       # back to event-local rows
+        # events with more rows than candidates: is the candidate list provably sufficient?
+        eps = (0.0 if b.bf16_exact else _EPS_BF16)
+        eps = eps + b.d * 1.2e-7
+        sizes = self._offsets_d[1:] - self._offsets_d[:-1]
+        kth = score[:, k - 1]
+        ok = (sizes <= kc) | ((idx[:, k - 1] >= 0) & (torch.isnan(kth) | (kth >= c_score[:, kc - 1] + eps)))
+        for j in torch.nonzero(~ok).reshape(-1).tolist():          # rare: straight from the event's own rows
+            o0, o1 = int(self.offsets[j]), int(self.offsets[j + 1])
+            ri, rs = search_rows(b.src[o0:o1], q, min(k, o1 - o0))
+            idx[j, : ri.numel()] = ri
+            score[j, : ri.numel()] = rs.to(torch.float32)
+        valid = idx >= 0
+        # np.max over the event's top-k as the reference takes it (hm:3156): NaN wins
+        mx = torch.where(valid, score, torch.full_like(score, float("-inf"))).max(dim=1).values
+        mx = torch.where((valid & torch.isnan(score)).any(dim=1), torch.full_like(mx, float("nan")), mx)
+        return idx, score, mx
 
     def recall_windows(self, idx: torch.Tensor, score: torch.Tensor, top: int = 5, pad: float = 1.0,
                        enabled: Optional[np.ndarray] = None):
@@ -237,7 +289,7 @@ class EventBank:
 
 def find_relevant_segments(query_features, events, bank: Optional[EventBank] = None, modality: str = "vision",
                            low_similarity: Optional[Callable] = None, top: int = 5, k: int = 5,
-                           pad: float = 1.0) -> List[SequenceSegment]:
+                           pad: float = 1.0, searched=None, segment_cls=None) -> List[SequenceSegment]:
     """Drop-in for the arithmetic of `_find_relevant_video_segments` (hm:3129-3279, modality
     "vision") and `_find_relevant_audio_segments` (hm:3281-3383, modality "audio").
 
@@ -251,7 +303,8 @@ def find_relevant_segments(query_features, events, bank: Optional[EventBank] = N
     events = list(events)
     if bank is None:
         bank = EventBank.from_events(events, modality)
-    idx_d, score_d, max_d = bank.search(query_features, k)
+    Seg = segment_cls or SequenceSegment                          # install() hands in the reference's own dataclass
+    idx_d, score_d, max_d = searched if searched is not None else bank.search(query_features, k)
     extra = []                                     # (similarity, position of the event, segments) from the callback
     enabled = np.ones(bank.nev, dtype=np.uint8)
     if low_similarity is not None:
@@ -280,11 +333,11 @@ def find_relevant_segments(query_features, events, bank: Optional[EventBank] = N
         if modality == "vision":                   # hm:3264-3271
             t = float(bank.times[bank.time_offsets[j] + rows[r]])
             ft = list(ev.frame_times)
-            seg = SequenceSegment(start_time=t0, end_time=t1,
-                                  frames=[ev.frames[i] for i in range(len(ev.frames)) if t - pad <= ft[i] <= t + pad],
-                                  frame_times=[x for x in ft if t - pad <= x <= t + pad])
+            seg = Seg(start_time=t0, end_time=t1,
+                      frames=[ev.frames[i] for i in range(len(ev.frames)) if t - pad <= ft[i] <= t + pad],
+                      frame_times=[x for x in ft if t - pad <= x <= t + pad])
         else:                                      # hm:3368-3372
-            seg = SequenceSegment(start_time=t0, end_time=t1, audio_data=None)
+            seg = Seg(start_time=t0, end_time=t1, audio_data=None)
         ranked.append((float(sims[r]), j, r, [seg]))
     if extra:
         # the callback's entries sit where the event sits in the reference's list: stable sort by similarity

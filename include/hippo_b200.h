@@ -134,12 +134,14 @@ hippo_status hippo_topk_rows(const void* rows, int32_t dtype, int64_t n, int32_t
  * Exact second stage behind the bf16 searches: the same expression for `kc` candidate rows per
  * query, from the ORIGINAL fp32 / fp64 rows (one warp per candidate).  cand_idx holds GLOBAL row
  * numbers (rows [row_base, row_base + n) are local; -1 or a foreign row yields key 0).
+ *   q, q_ld    queries [nq, d], row stride q_ld elements; q_ld = 0: ONE query shared by all nq
+ *              candidate lists (the per-event lists of hippo_topk_segmented)
  *   out_key    optional [nq, kc] uint64 order keys of the exact scores (feed hippo_topk_merge
  *              with nparts = 1 to re-rank)
  *   out_score  optional [nq, kc] fp64 exact scores
  */
 hippo_status hippo_rescore(const void* rows, int32_t dtype, int64_t n, int32_t d, int64_t ld,
-                           int64_t row_base, const void* q, int32_t q_dtype, int32_t nq,
+                           int64_t row_base, const void* q, int32_t q_dtype, int64_t q_ld, int32_t nq,
                            const int64_t* cand_idx, int32_t kc,
                            uint64_t* out_key, double* out_score, void* stream);
 

@@ -122,6 +122,42 @@ def main() -> None:
             out[f"recall_{name}_nframes"] = np.array([len(s.frames) for s in segs], dtype=np.int64)
             out[f"recall_{name}_frame_times"] = np.array([t for s in segs for t in s.frame_times], dtype=np.float64)
 
+    # ---- the same loops over a store that went through the reference's OWN save_theta_event / load_theta_event
+    # (JSON text and back: float64 rows, hm:334-335, hm:391) ----
+    import pathlib
+    import types
+
+    vo_, hm_, bp_ = ref.modules
+    with tempfile.TemporaryDirectory() as td:
+        m = object.__new__(hm_.HippocampalMemory)
+        m.events_dir = pathlib.Path(td) / "events"
+        m.events_dir.mkdir()
+        m.event_index, m.event_index_file, m.long_term_store = {}, pathlib.Path(td) / "event_index.json", []
+        for e in events:
+            # the consolidation code keeps the time tables INSIDE `features` under '<modality>_times' keys, which is
+            # where to_dict (hm:116-120) looks for them; the reload then files them under feature_times (hm:375-381)
+            te = hm_.ThetaEvent(features={**e.features, **e.feature_times}, feature_times=dict(e.feature_times), frames=e.frames,
+                                frame_times=e.frame_times, frame_captions=[], audio_times=[], audio_transcription=[],
+                                holistic_audio_transcription=[], summary="", start_time=float(e.start_time),
+                                end_time=float(e.end_time))
+            m.save_theta_event(te, "vid")
+        for event_id in list(m.event_index):
+            m.load_theta_event(event_id)
+        assert len(m.long_term_store) == len(events)
+        for e, te in zip(events, m.long_term_store):      # the JSON round trip is exact: float32 values held in float64
+            for k_, v in e.features.items():
+                assert te.features[k_].dtype == np.float64 and np.array_equal(te.features[k_], v.astype(np.float64))
+        rs2 = object.__new__(hm_.QARecallSystem)
+        rs2.memory = types.SimpleNamespace(long_term_store=m.long_term_store)
+        rs2._current_question = ""
+        for name, (modality, q) in queries.items():
+            fn = rs2._find_relevant_video_segments if modality == "vision" else rs2._find_relevant_audio_segments
+            segs = fn(torch.from_numpy(q))
+            out[f"recall_json_{name}_bounds"] = np.array([[s.start_time, s.end_time] for s in segs], dtype=np.float64).reshape(-1, 2)
+            if modality == "vision":
+                out[f"recall_json_{name}_nframes"] = np.array([len(s.frames) for s in segs], dtype=np.int64)
+                out[f"recall_json_{name}_frame_times"] = np.array([t for s in segs for t in s.frame_times], dtype=np.float64)
+
     # ---- key-frame pre-filter: the reference's own extract_frames_from_video (bp:116-260) on an MJPG AVI ----
     import hashlib
     import pathlib

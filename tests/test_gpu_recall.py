@@ -146,3 +146,96 @@ def test_edge_cases(cuda_device):
     assert 2 not in ev.tolist() and len(ev) == 5
     assert np.all(np.diff(sims) <= 0)
     assert np.array_equal(wins[:, 0], np.maximum(0.0, rows.astype(np.float64) - 1.0))
+
+
+def _json_store_events():
+    """What the reference's save_theta_event -> load_theta_event round trip yields for cases.recall_events()
+    (checked against the real reference in tests/golden/make_golden.py): float64 rows holding the float32 values."""
+    events, queries = cases.recall_events()
+    out = []
+    for e in events:
+        feats = {k: v.astype(np.float64) for k, v in e.features.items()}
+        out.append(cases._Event(feats, dict(e.feature_times), e.frames, e.frame_times))
+    return out, queries
+
+
+@pytest.mark.parametrize("name", ["v_in", "v_out", "v_mix", "a_in", "a_mix"])
+def test_event_store_hook_matches_reference_on_a_json_loaded_store(cuda_device, name):
+    """install(event_store=True)'s search path (store.find_segments: ONE cross-event bank, hippo_topk_segmented,
+    exact re-scoring from the float64 rows, hippo_recall_windows) against the committed outputs of the reference's
+    own _find_relevant_{video,audio}_segments run on a store that went through its JSON save / load."""
+    import types
+
+    from hippomm_b200 import store
+
+    events, queries = _json_store_events()
+    modality, q = queries[name]
+    g = cases.golden()
+    rs = types.SimpleNamespace(memory=types.SimpleNamespace(long_term_store=events))
+    segs = store.find_segments(rs, torch.from_numpy(q), modality)
+    bounds = np.array([[s.start_time, s.end_time] for s in segs], dtype=np.float64).reshape(-1, 2)
+    assert np.array_equal(bounds, g[f"recall_json_{name}_bounds"])
+    if modality == "vision":
+        assert np.array_equal(np.array([len(s.frames) for s in segs]), g[f"recall_json_{name}_nframes"])
+        assert np.array_equal(np.array([t for s in segs for t in s.frame_times]), g[f"recall_json_{name}_frame_times"])
+    bank = rs.memory.__dict__["_hippo_event_banks"][modality][1]
+    assert bank.bank.src.dtype == torch.float64                    # the rows are kept in the store's own precision
+    store.find_segments(rs, torch.from_numpy(q), modality)
+    assert rs.memory.__dict__["_hippo_event_banks"][modality][1] is bank      # built once per state of the store
+    rs.memory.long_term_store = events[:-1]
+    store.find_segments(rs, torch.from_numpy(q), modality)
+    assert rs.memory.__dict__["_hippo_event_banks"][modality][1] is not bank  # ... and rebuilt when it changes
+
+
+def test_event_store_hook_wiring_and_llm_delegation(cuda_device):
+    """install_event_store on a stand-in module with the reference's class layout: the wrapped recall methods answer
+    from the GPU bank, hand the call to the original method exactly when an event would take the LLM branch
+    (best similarity < 0.4 and captions present, hm:3156), and uninstall restores the originals."""
+    import types
+
+    from hippomm_b200 import SequenceSegment, store
+
+    events, queries = _json_store_events()
+    calls = []
+
+    class HippocampalMemory:
+        def load_theta_event(self, event_id):
+            return None
+
+        def save_theta_event(self, event, video_id):
+            return None
+
+    class QARecallSystem:
+        def _find_relevant_video_segments(self, query_features, optional_search_query=None):
+            calls.append("video")
+            return ["from the reference"]
+
+        def _find_relevant_audio_segments(self, query_features):
+            calls.append("audio")
+            return ["from the reference"]
+
+    fake = types.SimpleNamespace(HippocampalMemory=HippocampalMemory, QARecallSystem=QARecallSystem,
+                                 ThetaEvent=cases._Event, SequenceSegment=SequenceSegment)
+    saved = {}
+    store.install_event_store(fake, saved)
+    try:
+        rs = QARecallSystem()
+        rs.memory = types.SimpleNamespace(long_term_store=events)
+        g = cases.golden()
+        segs = rs._find_relevant_video_segments(torch.from_numpy(queries["v_mix"][1]))
+        assert not calls and all(isinstance(s, SequenceSegment) for s in segs)
+        assert np.array_equal(np.array([[s.start_time, s.end_time] for s in segs]), g["recall_json_v_mix_bounds"])
+        segs = rs._find_relevant_audio_segments(torch.from_numpy(queries["a_in"][1]))
+        assert not calls
+        assert np.array_equal(np.array([[s.start_time, s.end_time] for s in segs]), g["recall_json_a_in_bounds"])
+        # a query unrelated to every event scores below 0.4 everywhere; captions on one event -> the LLM branch
+        rng = np.random.default_rng(3)
+        far = torch.from_numpy(rng.standard_normal(1024).astype(np.float32))
+        assert rs._find_relevant_video_segments(far) != ["from the reference"] and not calls     # no captions: GPU path
+        events[2].frame_captions = ["a caption"]
+        assert rs._find_relevant_video_segments(far) == ["from the reference"] and calls == ["video"]
+        events[2].frame_captions = []
+        assert rs._find_relevant_video_segments(torch.zeros(7)) == []                          # hm:3135-3137
+    finally:
+        store.uninstall_event_store(saved)
+    assert QARecallSystem()._find_relevant_audio_segments(None) == ["from the reference"]
