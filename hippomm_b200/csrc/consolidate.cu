@@ -4,24 +4,29 @@
 // every KEPT earlier row j has sim(i, j) < gamma (hm:958-961).  Similarities against rows that were dropped
 // are never looked at -- and on video-like input most rows are dropped.  So the rows are processed in BANDS
 // of kConsBand rows, and a band is only contracted against
-//     (a) the rows kept so far, held compacted at the front of a second bf16 matrix Y, and
-//     (b) itself (lower triangle),
+//     (R) the rows kept so far, held compacted at the front of a second bf16 matrix Y  (a rectangle), and
+//     (T) itself                                                                        (a lower triangle),
 // which is exactly the set of pairs the greedy rule can consult.  With K rows kept out of N the tensor work
 // drops from N^2/2 to about N K / 2 + N band / 2 pairs (10x at 6% kept); when everything is kept it is the
 // full triangle again.  The decisions are identical either way.
 //
-//   0. hippo_bank_build       fp32 rows -> bf16 rows X + fp32 norms                (hm:951)
-//   per band (all asynchronous, the extent of a band's work is read from device memory):
-//   1. cons_advance_kernel    finishes the previous band (its kept rows are compacted to Y[K ..), K grows,
-//                             the caller's out_keep receives their row numbers) and copies this band's rows
-//                             to Y[K .. K + rows)
-//   2. sim_tc EPI_MASK        similarity bits of Y rows [K, K + rows) against Y rows before them, on tcgen05
-//                                                                                 (hm:952, hm:960)
-//   3. recheck_kernel         pairs within `band` of gamma re-evaluated from the fp32 rows
-//   4. greedy_scan_kernel     row i kept iff no kept j < i has bit (i, j)           (hm:958-961)
+// Only R depends on earlier decisions (it needs the kept rows of the band before), T does not -- so the
+// triangle of band b + 1 runs UNDER the decision chain of band b.  Two streams:
+//   tensor stream (internal)      T(0) rT(0) | R(0) T(1) rT(1) | R(1) T(2) rT(2) | ...
+//   caller's stream               bank build | rR(0) scan(0) compact(0) | rR(1) scan(1) compact(1) | ...
+//     T(b)        sim_tc EPI_MASK triangle of band b, rows straight from X (bf16 image of the caller's rows) ->
+//                 band-local bit matrix Mt[b & 1]; on 65 of the 74 CTA pairs, so that the chain's kernels find SMs
+//     R(b)        sim_tc EPI_MASK band b x Y[0, K) -> one conflict flag per band row             (hm:952, hm:960)
+//     rT / rR     pairs within `band` of gamma re-evaluated from the fp32 rows
+//     scan(b)     row i kept iff no kept row before it has its bit set: the flag of R(b) (all of Y is kept), then the
+//                 sequential part over Mt                                                        (hm:958-961)
+//     compact(b)  the band's kept rows are appended to Y, K grows, out_keep receives their row numbers
+// R(b + 1) waits for compact(b); everything else of band b + 1 is done by then.  All ordering is by stream events,
+// the extent of every launch is read from device memory (K), nothing synchronises with the host.
 //
-// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed; the bit matrix holds the rows of
-// the current band only ((band + 1024) x N / 8 bytes: 115 MB at N = 100k).
+// The N x N fp32 matrix of the reference (40 GB at N = 100k) is never formed: the triangle's bits live in two
+// band-local matrices (2 x 8 MB), and of the rectangle only the OR over a band row's bits is kept (one flag per
+// row: every column there is a kept row, so a single conflict settles the row).
 #include "common.cuh"
 #include "sim_tc.cuh"
 
@@ -33,27 +38,32 @@ namespace hippo {
 
 constexpr int kConsBandDefault = 8192;
 
-// ---- 3. exact re-evaluation of near-threshold pairs ---------------------------------
-// One warp per pair (i, j) of Y rows.  The rows are looked up in the caller's fp32 matrix through yidx,
-// normalised element-wise in fp32 exactly like hm:951 (x / |x| with the fp32 norm), the products are
-// accumulated in fp64, and the bit becomes !(sim < gamma) -- the best available stand-in for the
+// ---- exact re-evaluation of near-threshold pairs ---------------------------------
+// One warp per pair (i, j): i = row of the band (original row r0 + i), j = column -- a row of the same band
+// (triangle: original row r0 + j) or a row of Y (rectangle: original row yidx[j]).  The rows are taken from the
+// caller's fp32 matrix, normalised element-wise in fp32 exactly like hm:951 (x / |x| with the fp32 norm), the
+// products are accumulated in fp64, and the bit becomes !(sim < gamma) -- the best available stand-in for the
 // reference's fp32 sgemm value.
 __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ feats,
-                                                      const float* __restrict__ norm, int d,
-                                                      const int64_t* __restrict__ yidx,
+                                                      const float* __restrict__ norm, int d, int64_t r0,
+                                                      const int64_t* __restrict__ yidx /* null: triangle */,
                                                       float gamma, const uint2* __restrict__ pairs,
                                                       const int32_t* __restrict__ count, int32_t cap,
                                                       uint32_t* __restrict__ mask, int64_t words_per_row,
-                                                      const int32_t* __restrict__ dyn_k) {
-  const int64_t row0 = (int64_t)(*dyn_k / 512) * 512;     // first row held by the band-local bit matrix
+                                                      int32_t* __restrict__ rowhit /* rectangle */,
+                                                      int32_t* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int32_t np = *count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&stats[0], np < cap ? np : cap);
+    if (np > cap) atomicOr(&stats[1], 1);
+  }
   if (np > cap) np = cap;
   for (int64_t pi = warp; pi < np; pi += nwarps) {
     const uint2 pr = pairs[pi];
-    const int64_t ra = yidx[pr.x], rb = yidx[pr.y];
+    const int64_t ra = r0 + pr.x, rb = yidx ? yidx[pr.y] : r0 + pr.y;
     const float* a = feats + ra * d;
     const float* b = feats + rb * d;
     const float na = norm[ra], nb = norm[rb];
@@ -69,24 +79,25 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float* __restrict__ 
     acc = warp_sum(acc);
     if (lane == 0) {
       const bool bit = !(acc < (double)gamma);
-      uint32_t* w = mask + ((int64_t)pr.x - row0) * words_per_row + (pr.y >> 5);
-      const uint32_t m = 1u << (pr.y & 31);
-      if (bit) atomicOr(w, m); else atomicAnd(w, ~m);
+      if (rowhit != nullptr) {                       // rectangle: the column is a kept row, a conflict drops the band row
+        if (bit) rowhit[pr.x] = 1;
+      } else {                                       // triangle: the contraction left the bit clear
+        if (bit) atomicOr(mask + (int64_t)pr.x * words_per_row + (pr.y >> 5), 1u << (pr.y & 31));
+      }
     }
   }
 }
 
-// ---- 4. greedy scan over the bit matrix of one band --------------------------------------
-// Rows are numbered in Y space: rows [0, K) are final (kept), the band is [K, n), n = K + band_rows.  CTA x
-// owns the 512 rows of block b = K / 512 + x, one thread per row (rows of the first block that lie below K
-// are simply resolved again: kept rows never conflict with each other).  The chain over blocks is sequential
-// (a row's fate depends on which earlier rows were KEPT), so the kernel is bound by the hand-off latency
-// between consecutive blocks; everything that does not depend on the predecessors' results is done ahead:
+// ---- greedy scan over the bit matrices of one band --------------------------------------
+// A row of the band is dropped at once if any bit of its row of the RECTANGLE matrix is set (every row of Y is a kept
+// row, final).  The rest is the sequential part, over the band-local TRIANGLE matrix: CTA x owns band rows
+// [512 x, 512 x + 512), one thread per row.  The chain over blocks is sequential (a row's fate depends on which
+// earlier rows were KEPT), so the kernel is bound by the hand-off latency between consecutive blocks; everything
+// that does not depend on the predecessors' results is done ahead:
 //   * kept-words are published as self-validating 64-bit values (tag << 32 | word), so a consumer polls
 //     the data itself -- one L2 round trip per hand-off, no separate flag, no fence.  One warp per CTA
 //     polls, and CTAs far behind the frontier sleep between polls: a line hammered by every waiting warp
-//     of the grid delayed the publisher's store by ~5 us (profiles/).  Blocks below K need no polling:
-//     all their rows are kept;
+//     of the grid delayed the publisher's store by ~5 us (profiles/);
 //   * a thread holds its row's mask words against the block itself and its three predecessors in
 //     registers; blocks further back are folded in from global memory as they are published (they are
 //     final well before this block is on the critical path);
@@ -129,8 +140,9 @@ __device__ __forceinline__ uint32_t and_any16(const uint32_t (&words)[kScanWords
   return h;
 }
 
-__global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint32_t* __restrict__ mask,
+__global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint32_t* __restrict__ mask /*triangle*/,
                                                                       int64_t words_per_row,
+                                                                      const int32_t* __restrict__ rowhit,
                                                                       const int32_t* __restrict__ dyn_k, int band_rows,
                                                                       unsigned long long* kept /*[grid * 16], zeroed*/,
                                                                       unsigned long long* dbg) {
@@ -138,14 +150,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
   __shared__ __align__(16) uint32_t s_undec[2][kScanWords];
   __shared__ __align__(16) uint32_t s_kw[2][kScanWords];            // bulk ring
   __shared__ __align__(16) uint32_t s_pk[kScanPreds][kScanWords];   // predecessors' kept-words
-  const int kfinal = *dyn_k;
-  const int64_t n = (int64_t)kfinal + band_rows;
-  const int b0 = kfinal / kScanRows;               // first block of this launch; blocks below it are all kept
-  const int b = b0 + blockIdx.x;
+  (void)dyn_k;
+  const int64_t n = band_rows;
+  constexpr int b0 = 0;                            // blocks are numbered inside the band
+  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t row = (int64_t)blockIdx.x * kScanRows + tid;   // row of the band-local bit matrix (Y row - 512 b0)
+  const int64_t row = (int64_t)blockIdx.x * kScanRows + tid;   // row of the band
   if ((int64_t)b * kScanRows >= n) return;         // nobody waits for a block past the end
-  const bool live = (int64_t)b * kScanRows + tid < n;
+  const bool live = row < n;
   auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = now();
 
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
 #pragma unroll
     for (int j = 0; j < kScanPreds; ++j) pp[j][w] = 0;
   }
+  uint32_t hit = 0;
   if (live) {
     load_row_words(mask, words_per_row, row, b, dg);
 #pragma unroll
@@ -167,6 +180,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
 #pragma unroll
     for (int j = 0; j < kScanPreds; ++j)
       if (b - 1 - j >= 0) load_row_words(mask, words_per_row, row, b - 1 - j, pp[j]);
+    // a conflict with a row kept before this band (all of them final) drops the row: the rectangle kernel and the
+    // re-evaluation of its near-threshold pairs left one flag per band row
+    hit = (uint32_t)rowhit[row];
   }
   // a predecessor below b0 is already known (all kept): only predecessors of this launch can block a row
   bool blocked = false;
@@ -179,7 +195,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
   }
 
   // blocks 0 .. b-4 from global memory, one block (16 kept-words) per step; warp 0 polls
-  uint32_t hit = 0;
   const int nbulk = max(b - kScanPreds, 0);
   for (int g = 0; g < nbulk; ++g) {
     uint4 m[4];
@@ -277,13 +292,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) greedy_scan_kernel(const uint
   }
 }
 
-// ---- 1. finish the previous band, stage the next one -----------------------------------------
-// dyn[par_in] = K before the previous band, whose rows sit at Y[K, K + prev_rows) (original rows prev_r0 ..)
-// and whose kept-words are kept_prev (block-local: bit position = Y row - 512 * (K / 512)).  The kept rows
-// are compacted to Y[K, K'), out_keep[K ..) receives their original row numbers (ascending: hm:967), K' goes
-// to dyn[par_in ^ 1], and the next band's rows [next_r0, next_r0 + next_rows) are copied to Y[K', ...).
-// Everything is read from X (the bf16 image of the caller's rows), never from Y, so the compaction cannot
-// trample rows it still needs.  Every CTA recomputes the (short) prefix over the kept-words on its own.
+// ---- compaction of a band's kept rows -----------------------------------------
+// dyn[par_in] = K before the band, whose rows are X[r0, r0 + rows) and whose kept-words are kept_band (bit = row of
+// the band).  The kept rows are appended to Y[K, K'), out_keep[K ..) receives their original row numbers
+// (ascending: hm:967), K' goes to dyn[par_in ^ 1], and the kept-words of the band after next are cleared.
+// Every CTA recomputes the (short) prefix over the kept-words on its own.
 // one bf16 row, 16 bytes per lane and step, four loads in flight per lane
 __device__ __forceinline__ void copy_row(const uint4* __restrict__ sp, uint4* __restrict__ dp, int nvec, int lane) {
   int v = lane;
@@ -295,24 +308,20 @@ __device__ __forceinline__ void copy_row(const uint4* __restrict__ sp, uint4* __
 }
 
 constexpr int kAdvThreads = 256;
-constexpr int kAdvMaxWords = 1024;   // band of at most 32k - 512 rows
+constexpr int kAdvMaxWords = 1024;   // band of at most 32k rows
 
-__global__ void __launch_bounds__(kAdvThreads) cons_advance_kernel(
+__global__ void __launch_bounds__(kAdvThreads) cons_compact_kernel(
     const __nv_bfloat16* __restrict__ X, const float* __restrict__ xnorm, int d, __nv_bfloat16* __restrict__ Y,
-    float* __restrict__ ynorm, int64_t* __restrict__ yidx, const unsigned long long* __restrict__ kept_prev,
-    unsigned long long* __restrict__ kept_next, int kept_words, int32_t* dyn, int par_in, int64_t prev_r0,
-    int prev_rows, int64_t next_r0, int next_rows, int32_t* unc_count, int32_t unc_cap, int32_t* stats) {
+    float* __restrict__ ynorm, int64_t* __restrict__ yidx, const unsigned long long* __restrict__ kept_band,
+    unsigned long long* __restrict__ kept_clear, int kept_words, int32_t* dyn, int par_in, int64_t r0, int rows) {
   __shared__ int s_pref[kAdvMaxWords + 1];
   __shared__ uint32_t s_bits[kAdvMaxWords];
   const int tid = threadIdx.x, lane = tid & 31;
   const int K = dyn[par_in];
-  const int off = K - (K / kScanRows) * kScanRows;        // block-local position of Y row K
-  const int nwords = prev_rows > 0 ? (off + prev_rows + 31) / 32 : 0;
+  const int nwords = (rows + 31) / 32;
   for (int w = tid; w < nwords; w += kAdvThreads) {
-    uint32_t bits = (uint32_t)kept_prev[w];
-    if (w == off / 32) bits &= ~((1u << (off & 31)) - 1u);            // rows below K are old
-    if (w < off / 32) bits = 0;
-    const int end = off + prev_rows - w * 32;                          // rows past the band
+    uint32_t bits = (uint32_t)kept_band[w];
+    const int end = rows - w * 32;                                     // rows past the band
     if (end < 32) bits &= (1u << end) - 1u;
     s_bits[w] = bits;
   }
@@ -331,38 +340,22 @@ __global__ void __launch_bounds__(kAdvThreads) cons_advance_kernel(
     if (tid == 0) s_pref[nwords] = carry;
   }
   __syncthreads();
-  const int added = s_pref[nwords];
-  const int K2 = K + added;
+  const int K2 = K + s_pref[nwords];
 
   const int64_t warp = (int64_t)blockIdx.x * (kAdvThreads / 32) + (tid >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kAdvThreads / 32);
   const int vec_per_row = d / 8;                                       // 16-byte vectors per bf16 row
-  // compaction: one warp per kept row
-  for (int64_t t = warp; t < prev_rows; t += nwarps) {
-    const int pos = off + (int)t;
-    const uint32_t bits = s_bits[pos >> 5];
-    if (!((bits >> (pos & 31)) & 1u)) continue;
-    const int rank = s_pref[pos >> 5] + __popc(bits & ((1u << (pos & 31)) - 1u));
-    const int64_t src = prev_r0 + t, dst = (int64_t)K + rank;
+  for (int64_t t = warp; t < rows; t += nwarps) {                      // one warp per kept row
+    const uint32_t bits = s_bits[t >> 5];
+    if (!((bits >> (t & 31)) & 1u)) continue;
+    const int rank = s_pref[t >> 5] + __popc(bits & ((1u << (t & 31)) - 1u));
+    const int64_t src = r0 + t, dst = (int64_t)K + rank;
     copy_row(reinterpret_cast<const uint4*>(X + src * d), reinterpret_cast<uint4*>(Y + dst * d), vec_per_row, lane);
     if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
   }
-  // next band
-  for (int64_t t = warp; t < next_rows; t += nwarps) {
-    const int64_t src = next_r0 + t, dst = (int64_t)K2 + t;
-    copy_row(reinterpret_cast<const uint4*>(X + src * d), reinterpret_cast<uint4*>(Y + dst * d), vec_per_row, lane);
-    if (lane == 0) { ynorm[dst] = xnorm[src]; yidx[dst] = src; }
-  }
-  // the next band's hand-off words, the uncertain-pair list, the running statistics
   for (int64_t i = (int64_t)blockIdx.x * kAdvThreads + tid; i < kept_words; i += (int64_t)gridDim.x * kAdvThreads)
-    kept_next[i] = 0;
-  if (blockIdx.x == 0 && tid == 0) {
-    dyn[par_in ^ 1] = K2;
-    const int32_t c = *unc_count;
-    stats[0] += c < unc_cap ? c : unc_cap;
-    if (c > unc_cap) stats[1] = 1;
-    *unc_count = 0;
-  }
+    kept_clear[i] = 0;
+  if (blockIdx.x == 0 && tid == 0) dyn[par_in ^ 1] = K2;
 }
 
 __global__ void cons_finish_kernel(const int32_t* dyn, int par, const int32_t* inexact, const int32_t* stats,
@@ -376,8 +369,9 @@ __global__ void iota_kernel(int64_t n, int64_t* out_keep, int32_t* out_count) {
   if (threadIdx.x == 0) *out_count = (int32_t)n;
 }
 
-// HIPPO_CONS_TIMING: CUDA-event time of every launch of the last hippo_consolidate call on this thread, summed per
-// stage {mask (tcgen05), recheck, scan, advance / staging / bank build}; read back with hippo_debug_consolidate_timing
+// HIPPO_CONS_TIMING: CUDA-event time per stage of the last hippo_consolidate call on this thread
+// {T + R launches on the tensor stream, fp32 re-evaluation, greedy scan, bank build + compaction}; with the stages
+// overlapped the four do not add up to the call's duration any more.  Read with hippo_debug_consolidate_timing.
 static thread_local double g_cons_ms[4] = {0, 0, 0, 0};
 
 static int cons_band(int requested = 0) {
@@ -391,19 +385,21 @@ static int cons_band(int requested = 0) {
 struct ConsLayout {
   __nv_bfloat16* X;        // bf16 image of the caller's rows
   float* xnorm;
-  __nv_bfloat16* Y;        // kept rows so far, compacted, followed by the current band
+  __nv_bfloat16* Y;        // kept rows so far, compacted
   float* ynorm;
-  uint32_t* mask;          // bit matrix of the current band: row = Y row - 512 (K / 512), columns in Y row numbers
-  int64_t words_per_row;
-  unsigned long long* kept[2];   // block-local tagged kept-words of the current / next band
+  uint32_t* mt[2];         // triangle bit matrix of a band (band-local rows and columns), two bands in flight
+  int64_t mt_words;
+  int32_t* rowhit;         // rectangle: one flag per band row (conflict with a row kept before the band)
+  unsigned long long* kept[2];   // tagged kept-words of the current / next band
   int kept_words;
-  uint2* unc;
+  uint2* unc_t;            // near-threshold pairs of the triangle / of the rectangle
+  uint2* unc_r;
   int32_t unc_cap;
-  int32_t* counters;       // [0] uncertain count, [2] inexact, [4..5] dyn K (two parities), [8..11] running stats
+  int32_t* counters;       // [0] triangle list count, [1] rectangle list count, [2] inexact, [4..5] dyn K (two parities), [8..11] statistics
   size_t bytes;
 };
 
-// default capacity of the near-threshold pair list (drained after every band)
+// default capacity of the near-threshold pair lists (each drained after every band)
 static int64_t cons_default_cap(int64_t n, int band) {
   return 64 * ((n < (int64_t)band ? n : (int64_t)band) + 1024) + (1 << 20);
 }
@@ -415,21 +411,39 @@ static ConsLayout cons_layout(void* ws, size_t ws_bytes, int64_t n, int d, int b
   L.xnorm = c.take<float>((size_t)n);
   L.Y = c.take<__nv_bfloat16>((size_t)n * d);
   L.ynorm = c.take<float>((size_t)n);
-  L.words_per_row = (n + kTcBN - 1) / kTcBN * (kTcBN / 32);
-  // the current band only: rows [512 (K / 512), K + band) rounded up to the 256-row blocks the contraction writes
-  const int64_t mask_rows = (n < (int64_t)band ? n : (int64_t)band) + 1024;
-  L.mask = c.take<uint32_t>((size_t)mask_rows * L.words_per_row);
+  const int64_t brows = n < (int64_t)band ? n : (int64_t)band;
+  const int64_t brows_pad = (brows + kTcBN - 1) / kTcBN * kTcBN;          // the contraction writes whole 256-row blocks' rows < na only, pad anyway
+  L.mt_words = (brows + kScanRows - 1) / kScanRows * kScanWords;         // whole 512-column scan blocks
+  L.mt[0] = c.take<uint32_t>((size_t)brows_pad * L.mt_words);
+  L.mt[1] = c.take<uint32_t>((size_t)brows_pad * L.mt_words);
+  L.rowhit = c.take<int32_t>((size_t)brows_pad);
   L.kept_words = (band / kScanRows + 1) * kScanWords;
   L.kept[0] = c.take<unsigned long long>((size_t)L.kept_words);
   L.kept[1] = c.take<unsigned long long>((size_t)L.kept_words);
-  // the list is drained after every band
   int64_t cap = unc_cap > 0 ? unc_cap : cons_default_cap(n, band);
   if (cap > 0x7fffff00ll) cap = 0x7fffff00ll;
   L.unc_cap = (int32_t)cap;
-  L.unc = c.take<uint2>((size_t)cap);
+  L.unc_t = c.take<uint2>((size_t)cap);
+  L.unc_r = c.take<uint2>((size_t)cap);
   L.counters = c.take<int32_t>(64);
   L.bytes = c.used();
   return L;
+}
+
+// the internal tensor stream and the events that order it against the caller's stream: created once per host thread
+static cudaStream_t cons_side_stream() {
+  static thread_local cudaStream_t st = nullptr;
+  if (st == nullptr && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+  return st;
+}
+static cudaEvent_t cons_event(size_t i) {
+  static thread_local std::vector<cudaEvent_t> pool;
+  while (pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    pool.push_back(e);
+  }
+  return pool[i];
 }
 
 }  // namespace hippo
@@ -475,70 +489,175 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
     set_error("hippo_consolidate: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;
   }
+  cudaStream_t ts = cons_side_stream();
+  HIPPO_REQUIRE(ts != nullptr, "hippo_consolidate: could not create the internal stream");
+  // HIPPO_CONS_OVERLAP=0: everything on the caller's stream, in dependency order (debugging aid)
+  const bool overlap = !(getenv("HIPPO_CONS_OVERLAP") && atoi(getenv("HIPPO_CONS_OVERLAP")) == 0);
+  if (!overlap) ts = s;
+  size_t nev = 0;
+  auto next_event = [&]() { return cons_event(nev++); };
+
+  const bool timing = getenv("HIPPO_CONS_TIMING") != nullptr;
+  struct Span { cudaEvent_t a, b; int stage; };
+  std::vector<Span> spans;
+  auto span_begin = [&](cudaStream_t q, int stage) -> int {
+    if (!timing) return -1;
+    Span sp{};
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    sp.stage = stage;
+    cudaEventRecord(sp.a, q);
+    spans.push_back(sp);
+    return (int)spans.size() - 1;
+  };
+  auto span_end = [&](cudaStream_t q, int id) { if (id >= 0) cudaEventRecord(spans[id].b, q); };
+
+  int sp = span_begin(s, 3);
   HIPPO_CUDA(cudaMemsetAsync(L.counters, 0, 64 * sizeof(int32_t), s));
+  HIPPO_CUDA(cudaMemsetAsync(L.kept[0], 0, (size_t)L.kept_words * 8, s));
+  HIPPO_CUDA(cudaMemsetAsync(L.kept[1], 0, (size_t)L.kept_words * 8, s));
+  HIPPO_CUDA(cudaMemsetAsync(L.rowhit, 0, (size_t)(n < band ? n : band) * sizeof(int32_t), s));   // band 0 has no rectangle
   st = hippo_bank_build(feats, HIPPO_F32, n, d, d, L.X, L.xnorm, L.counters + 2, stream);
   if (st != HIPPO_OK) return st;
+  span_end(s, sp);
   int32_t* dyn = L.counters + 4;
   int32_t* stats = L.counters + 8;
+  cudaEvent_t e0 = next_event();
+  HIPPO_REQUIRE(e0 != nullptr, "hippo_consolidate: could not create events");
+  if (overlap) {
+    HIPPO_CUDA(cudaEventRecord(e0, s));
+    HIPPO_CUDA(cudaStreamWaitEvent(ts, e0, 0));
+  }
 
   TcMaskArgs a{};
-  a.feats_bf16 = L.Y;
-  a.norm = L.ynorm;
-  a.n = n;
+  a.a_rows = L.X;
+  a.a_total = n;
   a.d = d;
   a.gamma = gamma;
   a.band_exact = band_exact;
   a.band_inexact = band_inexact;
   a.inexact = L.counters + 2;
-  a.mask = L.mask;
-  a.words_per_row = L.words_per_row;
-  a.uncertain = L.unc;
-  a.uncertain_count = L.counters + 0;
   a.uncertain_cap = L.unc_cap;
 
-  const int adv_grid = sm_count() * 8;
+  const int compact_grid = sm_count() * 2;
   const int scan_grid = band / kScanRows + 1;
+  const int nbands = (int)((n + band - 1) / band);
   const bool dbg_on = getenv("HIPPO_SCAN_DEBUG") != nullptr;
-  const bool timing = getenv("HIPPO_CONS_TIMING") != nullptr;
-  struct Stamp { cudaEvent_t e; int stage; };
-  std::vector<Stamp> stamps;
-  auto stamp = [&](int stage) {           // stage = what ran SINCE the previous stamp
-    if (!timing) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, s);
-    stamps.push_back({e, stage});
+  // the triangle kernels run beside the chain's kernels (scan: up to 17 CTAs of 512 threads; re-evaluation and
+  // compaction: many short CTAs), which do not fit on an SM next to a tcgen05 CTA: leave them a few SMs
+  const int pairs_all = sm_count() / 2;
+  int pairs_t = 0;
+  if (overlap && nbands > 1 && pairs_all > 12) {
+    // the fewest pairs that still finish the triangle's tiles in as few rounds as the whole machine would need
+    // (528 tiles of an 8,192-row band: 8 rounds on 74 pairs -- and on 66); if that leaves the chain fewer than four
+    // pairs' SMs, one round more
+    const int hb = (int)(((n < band ? n : band) + kTcBN - 1) / kTcBN);
+    const int tiles = hb * (hb + 1) / 2;
+    int rounds = (tiles + pairs_all - 1) / pairs_all;
+    pairs_t = (tiles + rounds - 1) / rounds;
+    if (pairs_t > pairs_all - 4) { ++rounds; pairs_t = (tiles + rounds - 1) / rounds; }
+    if (pairs_t < 1) pairs_t = 1;
+  }
+
+  // T(b) + its re-evaluation on the tensor stream; the bit matrix Mt[b & 1] was last read by scan(b - 2)
+  std::vector<cudaEvent_t> e_scan(nbands, nullptr);
+  auto launch_triangle = [&](int b) -> hippo_status {
+    const int64_t r0 = (int64_t)b * band;
+    const int rows = (int)(n - r0 < band ? n - r0 : band);
+    if (overlap && b >= 2) HIPPO_CUDA(cudaStreamWaitEvent(ts, e_scan[b - 2], 0));
+    int id = span_begin(ts, 0);
+    HIPPO_CUDA(cudaMemsetAsync(L.counters + 0, 0, sizeof(int32_t), ts));
+    TcMaskArgs t = a;
+    t.rect = false;
+    t.b_rows = L.X;
+    t.b_total = n;
+    t.a_row0 = t.b_row0 = r0;
+    t.na = rows;
+    t.anorm = t.bnorm = L.xnorm + r0;
+    t.dyn_k = nullptr;
+    t.mask = L.mt[b & 1];
+    t.words_per_row = L.mt_words;
+    t.uncertain = L.unc_t;
+    t.uncertain_count = L.counters + 0;
+    t.max_pairs = pairs_t;
+    hippo_status r = tc_mask_launch(t, ts);
+    if (r != HIPPO_OK) return r;
+    span_end(ts, id);
+    id = span_begin(ts, 1);
+    recheck_kernel<<<sm_count() * 2, 256, 0, ts>>>(feats, L.xnorm, d, r0, nullptr, gamma, L.unc_t, L.counters + 0, L.unc_cap,
+                                                   L.mt[b & 1], L.mt_words, nullptr, stats);
+    HIPPO_CUDA(cudaGetLastError());
+    span_end(ts, id);
+    return HIPPO_OK;
   };
-  stamp(3);
-  int par = 1;                      // dyn[par] = K before the band being finished
-  int64_t prev_r0 = 0;
-  int prev_rows = 0;
-  int iband = 0;
-  for (int64_t r0 = 0;; r0 += band, ++iband) {
-    const int rows = (int)(r0 < n ? (n - r0 < band ? n - r0 : band) : 0);
-    // kept-words: band i publishes into kept[i & 1]; the advance after band i-1 reads kept[(i-1) & 1] and clears kept[i & 1]
-    cons_advance_kernel<<<adv_grid, kAdvThreads, 0, s>>>(L.X, L.xnorm, d, L.Y, L.ynorm, out_keep,
-                                                         L.kept[(iband + 1) & 1], L.kept[iband & 1], L.kept_words, dyn,
-                                                         par, prev_r0, prev_rows, r0, rows, L.counters + 0, L.unc_cap,
-                                                         stats);
-    HIPPO_CUDA(cudaGetLastError());
-    stamp(3);
-    par ^= 1;                       // dyn[par] = K before this band
-    if (rows == 0) break;
-    a.dyn_k = dyn + par;
-    a.band_rows = rows;
-    st = tc_mask_launch(a, s);
-    if (st != HIPPO_OK) return st;
-    stamp(0);
-    recheck_kernel<<<sm_count() * 4, 256, 0, s>>>(feats, L.xnorm, d, out_keep, gamma, L.unc, L.counters + 0,
-                                                   L.unc_cap, L.mask, L.words_per_row, dyn + par);
-    HIPPO_CUDA(cudaGetLastError());
-    stamp(1);
+
+  st = launch_triangle(0);
+  if (st != HIPPO_OK) return st;
+  int par = 0;                      // dyn[par] = K before the band being processed (0 for the first)
+  for (int b = 0; b < nbands; ++b) {
+    const int64_t r0 = (int64_t)b * band;
+    const int rows = (int)(n - r0 < band ? n - r0 : band);
+    // ---- tensor stream: R(b) (needs compact(b - 1): the caller's stream is joined first), then T(b + 1) ----
+    if (b > 0) {
+      if (overlap) {
+        cudaEvent_t ec = next_event();
+        HIPPO_REQUIRE(ec != nullptr, "hippo_consolidate: could not create events");
+        HIPPO_CUDA(cudaEventRecord(ec, s));
+        HIPPO_CUDA(cudaStreamWaitEvent(ts, ec, 0));
+      }
+      int id = span_begin(ts, 0);
+      HIPPO_CUDA(cudaMemsetAsync(L.counters + 1, 0, sizeof(int32_t), ts));
+      HIPPO_CUDA(cudaMemsetAsync(L.rowhit, 0, (size_t)rows * sizeof(int32_t), ts));
+      TcMaskArgs r = a;
+      r.rect = true;
+      r.b_rows = L.Y;
+      r.b_total = n;
+      r.a_row0 = r0;
+      r.b_row0 = 0;
+      r.na = rows;
+      r.anorm = L.xnorm + r0;
+      r.bnorm = L.ynorm;
+      r.dyn_k = dyn + par;
+      r.mask = nullptr;
+      r.words_per_row = 0;
+      r.rowhit = L.rowhit;
+      r.uncertain = L.unc_r;
+      r.uncertain_count = L.counters + 1;
+      r.max_pairs = 0;
+      st = tc_mask_launch(r, ts);
+      if (st != HIPPO_OK) return st;
+      span_end(ts, id);
+    }
+    if (overlap) {
+      cudaEvent_t er = next_event();
+      HIPPO_REQUIRE(er != nullptr, "hippo_consolidate: could not create events");
+      HIPPO_CUDA(cudaEventRecord(er, ts));          // T(b), its re-evaluation and R(b) are done
+      HIPPO_CUDA(cudaStreamWaitEvent(s, er, 0));
+    }
+    if (b + 1 < nbands) {
+      st = launch_triangle(b + 1);
+      if (st != HIPPO_OK) return st;
+    }
+    // ---- caller's stream: re-evaluation of R(b), scan(b), compact(b) ----
+    if (b > 0) {
+      int id = span_begin(s, 1);
+      recheck_kernel<<<sm_count() * 2, 256, 0, s>>>(feats, L.xnorm, d, r0, out_keep, gamma, L.unc_r, L.counters + 1, L.unc_cap,
+                                                    nullptr, 0, L.rowhit, stats);
+      HIPPO_CUDA(cudaGetLastError());
+      span_end(s, id);
+    }
     unsigned long long* dbg = nullptr;
     if (dbg_on) { cudaMalloc(&dbg, (size_t)scan_grid * 64); cudaMemset(dbg, 0, (size_t)scan_grid * 64); }
-    greedy_scan_kernel<<<scan_grid, kScanThreads, 0, s>>>(L.mask, L.words_per_row, dyn + par, rows, L.kept[iband & 1], dbg);
+    int id = span_begin(s, 2);
+    greedy_scan_kernel<<<scan_grid, kScanThreads, 0, s>>>(L.mt[b & 1], L.mt_words, L.rowhit, dyn + par, rows,
+                                                          L.kept[b & 1], dbg);
     HIPPO_CUDA(cudaGetLastError());
-    stamp(2);
+    span_end(s, id);
+    if (overlap) {
+      e_scan[b] = next_event();
+      HIPPO_REQUIRE(e_scan[b] != nullptr, "hippo_consolidate: could not create events");
+      HIPPO_CUDA(cudaEventRecord(e_scan[b], s));
+    }
     if (dbg) {
       cudaStreamSynchronize(s);
       std::vector<unsigned long long> h((size_t)scan_grid * 8);
@@ -546,26 +665,33 @@ hippo_status hippo_consolidate_ex(const float* feats, int64_t n, int32_t d, floa
       cudaFree(dbg);
       const unsigned long long t0 = h[0];
       for (int i = 0; i < scan_grid; ++i)
-        if (iband % 8 == 0 && h[i * 8 + 3])
+        if (b % 8 == 0 && h[i * 8 + 3])
           fprintf(stderr, "[scan] band %d blk %2d start %7.2f bulk_done %7.2f phaseA %7.2f (%llu rounds) preds %7.2f published %7.2f us (rounds %llu)\n",
-                  iband, i, (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 5] - t0) / 1e3, h[i * 8 + 6],
+                  b, i, (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 5] - t0) / 1e3, h[i * 8 + 6],
                   (h[i * 8 + 2] - t0) / 1e3, (h[i * 8 + 3] - t0) / 1e3, h[i * 8 + 4]);
     }
-    prev_r0 = r0;
-    prev_rows = rows;
+    id = span_begin(s, 3);
+    // kept-words: band b publishes into kept[b & 1]; this launch reads them and clears the OTHER buffer for band
+    // b + 1 (last read by compact(b - 1), which is done)
+    cons_compact_kernel<<<compact_grid, kAdvThreads, 0, s>>>(L.X, L.xnorm, d, L.Y, L.ynorm, out_keep, L.kept[b & 1],
+                                                             L.kept[(b + 1) & 1], L.kept_words, dyn, par, r0, rows);
+    HIPPO_CUDA(cudaGetLastError());
+    span_end(s, id);
+    par ^= 1;
   }
   cons_finish_kernel<<<1, 1, 0, s>>>(dyn, par, L.counters + 2, stats, out_count, out_stats);
   HIPPO_CUDA(cudaGetLastError());
   if (timing) {
-    stamp(3);
     cudaStreamSynchronize(s);
+    cudaStreamSynchronize(ts);
     for (double& v : g_cons_ms) v = 0.0;
-    for (size_t i = 1; i < stamps.size(); ++i) {
+    for (auto& x : spans) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, stamps[i - 1].e, stamps[i].e);
-      g_cons_ms[stamps[i].stage] += ms;
+      cudaEventElapsedTime(&ms, x.a, x.b);
+      g_cons_ms[x.stage] += ms;
+      cudaEventDestroy(x.a);
+      cudaEventDestroy(x.b);
     }
-    for (auto& x : stamps) cudaEventDestroy(x.e);
   }
   return HIPPO_OK;
 }

@@ -66,13 +66,21 @@ struct TcParams {
   unsigned long long* counters;  // profiling (debug & 64): [0] slow-chunk calls, [1] insertions, [2] cycles in the
                                  // slow path (per warp), [3] cycles epilogue warps wait for accumulators, [4] epilogue tiles x warps,
                                  // [5] cycles the MMA thread waits for TMEM, [6] cycles it waits for operands
-  // mask
-  const int32_t* dyn_k;   // banded consolidation: rows [0, *dyn_k) of B are final (kept); A rows [*dyn_k, *dyn_k + band_rows)
-  int band_rows, i0;      // i0: first 256-row block to compute (set on the device from *dyn_k)
+  // mask (consolidation).  Two shapes, both with A = rows [a_row0, a_row0 + na) of the bf16 image X of the caller's
+  // rows (one band) and bits written band-locally (row = A row - a_row0):
+  //   mask_rect == 0  TRIANGLE: B = the same rows; column tiles t <= row block; bit (i, j) kept for j < i
+  //   mask_rect == 1  RECTANGLE: B = the first *dyn_k rows of Y (the rows kept so far, compacted); every column tile,
+  //                   bits of columns >= *dyn_k cleared (those rows of Y are stale)
+  int mask_rect;
+  const int32_t* dyn_k;   // rectangle: device count of kept rows = valid rows of B
+  int na;                 // rows of A (the band)
+  int64_t a_row0, b_row0; // first row of A / B inside their tensor maps
+  const float* anorm;     // norms of the A rows (already offset: anorm[0] belongs to row a_row0)
   float gamma, band_exact, band_inexact;
   const int32_t* inexact;
-  uint32_t* mask;
+  uint32_t* mask;         // triangle: bit matrix
   int64_t words_per_row;
+  int32_t* rowhit;        // rectangle: [na] set to 1 for a band row that conflicts with a kept row for certain
   uint2* uncertain;
   int32_t* uncertain_count;
   int32_t uncertain_cap;
@@ -93,50 +101,22 @@ __device__ __forceinline__ void decode_unit(const TcParams& p, int unit, int& m_
     m_base = 2 * (unit - split * p.m_pairs);
     t0 = split * p.tiles_per_split;
     t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-  } else if (p.dyn_k != nullptr) {
-    // banded consolidation: row blocks [i0, n_tiles) against column tiles t <= I, column tile slowest so the
-    // pairs running concurrently share it.  h row blocks; t < i0: all of them, then the triangle of the band.
-    const int h = p.n_tiles - p.i0;
-    const int rect = p.i0 * h;
-    int I;
-    if (unit < rect) {
-      t0 = unit / h;
-      I = p.i0 + (unit - t0 * h);
-    } else {
-      int r = unit - rect, j = 0;
-      while (r >= h - j) { r -= h - j; ++j; }
-      t0 = p.i0 + j;
-      I = t0 + r;
-    }
+  } else if (p.mask_rect) {
+    // rectangle: h row blocks of the band against every column tile of the kept rows, column tile slowest so that
+    // the pairs running concurrently share it
+    const int h = (p.na + kTcBN - 1) / kTcBN;
+    t0 = unit / h;
+    m_base = 2 * (unit - t0 * h);
     t1 = t0 + 1;
-    m_base = 2 * I;
     split = 0;
   } else {
-    // lower triangle of 256 x 256 blocks (t <= I), enumerated in BANDS of kBand row blocks: inside a band the
-    // column tile t varies slowest, so the pairs running concurrently share ~9 column tiles and the band's
-    // kBand row blocks; every column tile is then fetched from HBM once per band instead of once per row block.
-    constexpr int kBand = 8;
-    const int nI = p.n_tiles;                         // row blocks = column tiles
-    // units before band b: sum_{b'<b} (64 b' + 36) = 32 b^2 + 4 b   (full bands of 8 row blocks)
-    int b = (int)((sqrtf(16.f + 128.f * (float)unit) - 4.f) * (1.f / 64.f));
-    while ((int64_t)32 * (b + 1) * (b + 1) + 4 * (b + 1) <= unit) ++b;
-    while ((int64_t)32 * b * b + 4 * b > unit) --b;
-    const int h = min(kBand, nI - kBand * b);         // height of this band (the last one may be short)
-    int r = unit - (32 * b * b + 4 * b);
-    const int full = (kBand * b + 1) * h;             // t = 0 .. 8b: all h row blocks
-    int I;
-    if (r < full) {
-      t0 = r / h;
-      I = kBand * b + (r - t0 * h);
-    } else {
-      r -= full;                                      // tail: t = 8b + 1 + j has h - 1 - j row blocks
-      int j = 0;
-      while (r >= h - 1 - j) { r -= h - 1 - j; ++j; }
-      t0 = kBand * b + 1 + j;
-      I = t0 + r;
-    }
+    // triangle of the band's h row blocks (t <= I), column tile slowest
+    const int h = (p.na + kTcBN - 1) / kTcBN;
+    int r = unit, j = 0;
+    while (r >= h - j) { r -= h - j; ++j; }
+    t0 = j;
+    m_base = 2 * (j + r);
     t1 = t0 + 1;
-    m_base = 2 * I;
     split = 0;
   }
 }
@@ -251,13 +231,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   TcParams pm;
   if constexpr (EPI == EPI_MASK) {
     pm = p_in;
-    if (p_in.dyn_k != nullptr) {
-      const int kfinal = *p_in.dyn_k;
-      pm.n = (int64_t)kfinal + p_in.band_rows;
-      pm.i0 = 2 * (kfinal / 512);               // whole 512-row scan blocks are recomputed
+    const int h = (p_in.na + kTcBN - 1) / kTcBN;
+    if (p_in.mask_rect) {
+      pm.n = *p_in.dyn_k;                                  // valid rows of B = rows kept so far
       pm.n_tiles = (int)((pm.n + kTcBN - 1) / kTcBN);
-      const int h = pm.n_tiles - pm.i0;
-      pm.units = pm.i0 * h + h * (h + 1) / 2;
+      pm.units = pm.n_tiles * h;
+    } else {
+      pm.n = p_in.na;
+      pm.n_tiles = h;
+      pm.units = h * (h + 1) / 2;
     }
   }
   const TcParams& p = [&]() -> const TcParams& {
@@ -349,8 +331,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (rank == 0) mbar_arrive(&full[stage]);
           } else {
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes);   // bytes landing in both CTAs
-            tma_load_2d_pair(sa, &tmA, leader_full, kb * kTcBK, (x.m_base + (int)rank) * kTcBM);
-            tma_load_2d_pair(sa + kABytes, &tmB, leader_full, kb * kTcBK, x.t * kTcBN + (int)rank * (kTcBN / 2));
+            int32_t ra = (x.m_base + (int)rank) * kTcBM, rb = x.t * kTcBN + (int)rank * (kTcBN / 2);
+            if constexpr (EPI == EPI_MASK) { ra += (int32_t)p.a_row0; rb += (int32_t)p.b_row0; }
+            tma_load_2d_pair(sa, &tmA, leader_full, kb * kTcBK, ra);
+            tma_load_2d_pair(sa + kABytes, &tmB, leader_full, kb * kTcBK, rb);
           }
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
@@ -428,7 +412,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (x.first) pf_rown = r < p.nq ? p.qnorm[r] : 1.f;
         pf_thr = r < p.nq ? __ldcg(&p.thr_ord[r]) : 0u;
       } else {
-        if (x.first) pf_rown = r < p.n ? p.bnorm[r] : 0.f;
+        if (x.first) pf_rown = r < p.na ? p.anorm[r] : 0.f;
       }
     };
     if (have) prefetch(cur);
@@ -449,7 +433,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int i = 0; i < kListRegs; ++i) list[i] = 0;
           kth_key = 0;
         } else {
-          valid = arow < p.n;
+          valid = arow < p.na;
           const float ni = valid ? pf_rown : 0.f;
           const bool ok = ni > 0.f && ni < INFINITY;
           g_i = ok ? p.gamma * ni : -INFINITY;   // zero / non-finite row: every sim is NaN -> bit set
@@ -599,16 +583,17 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 }
               }
               w |= spec;                                  // NaN similarity: `NaN < gamma` is False (hm:960)
-              // keep pairs j < i only
+              // triangle: pairs j < i only; rectangle: columns below the number of kept rows only
               const int64_t jb = col0 + c * 32;
+              const int64_t jend = p.mask_rect ? p.n : arow;
               uint32_t keep;
-              if (!valid || jb >= arow) keep = 0u;
-              else if (jb + 32 <= arow) keep = 0xffffffffu;
-              else keep = (1u << (uint32_t)(arow - jb)) - 1u;
-              if (c2 == 0) { if (hh == 0) words[0] = w & keep; else words[1] = w & keep; }
-              else { if (hh == 0) words[2] = w & keep; else words[3] = w & keep; }
+              if (!valid || jb >= jend) keep = 0u;
+              else if (jb + 32 <= jend) keep = 0xffffffffu;
+              else keep = (1u << (uint32_t)(jend - jb)) - 1u;
+              uint32_t wk = w & keep;
               if (unc && keep) {
-                // rare path: pairs inside the band go to the uncertain list (re-evaluated from fp32 rows)
+                // rare path: pairs inside the band go to the uncertain list (re-evaluated from fp32 rows, which then
+                // sets their bit); a pair that does not fit the list keeps its tensor-core bit (and is reported)
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const float4 iv = inv4[j4];
@@ -619,11 +604,16 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const float d = fmaf(__uint_as_float(cur_r[j]), ivs[jj], -g_i);
                     if ((fabsf(d) <= b_i) && ((keep >> j) & 1u)) {
                       const int pos = atomicAdd(p.uncertain_count, 1);
-                      if (pos < p.uncertain_cap) p.uncertain[pos] = make_uint2((uint32_t)arow, (uint32_t)(jb + j));
+                      if (pos < p.uncertain_cap) {
+                        p.uncertain[pos] = make_uint2((uint32_t)arow, (uint32_t)(jb + j));
+                        wk &= ~(1u << j);
+                      }
                     }
                   }
                 }
               }
+              if (c2 == 0) { if (hh == 0) words[0] = wk; else words[1] = wk; }
+              else { if (hh == 0) words[2] = wk; else words[3] = wk; }
             }
           }
         }
@@ -634,9 +624,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr[buf]);
       if constexpr (EPI == EPI_MASK) {
         if (valid) {
-          // banded mode: the bit matrix holds the current band only, rows numbered from the first row block computed
-          uint4* dst = reinterpret_cast<uint4*>(p.mask + (arow - (int64_t)p.i0 * kTcBN) * p.words_per_row + (int64_t)t * 8 + chalf * 4);
-          *dst = make_uint4(words[0], words[1], words[2], words[3]);
+          if (p.mask_rect) {
+            // rectangle: every column is a row that was KEPT, so one conflict settles the band row; nobody needs the
+            // individual bits (every writer stores the same 1)
+            if ((words[0] | words[1] | words[2] | words[3]) != 0u) p.rowhit[arow] = 1;
+          } else {
+            // band-local bit matrix: row = row of the band, 8 words per column tile
+            uint4* dst = reinterpret_cast<uint4*>(p.mask + arow * p.words_per_row + (int64_t)t * 8 + chalf * 4);
+            *dst = make_uint4(words[0], words[1], words[2], words[3]);
+          }
         }
       } else {
         const bool last = !have_next || nxt.first;
@@ -717,10 +713,12 @@ static int debug_flags() {
 }
 
 template <int EPI>
-static hippo_status launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+static hippo_status launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s,
+                           int max_pairs = 0) {
   HIPPO_CUDA(cudaFuncSetAttribute(sim_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemBytes));
   int pairs = sm_count() / 2;                 // one CTA per SM, two SMs per 256-row tile
+  if (max_pairs > 0 && pairs > max_pairs) pairs = max_pairs;
   if (pairs > p.units) pairs = p.units;
   if (pairs < 1) return HIPPO_OK;
   sim_tc_kernel<EPI><<<2 * pairs, kTcThreads, kSmemBytes, s>>>(tmA, tmB, p);
@@ -786,18 +784,27 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
 
 hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   CUtensorMap tmA, tmB;
-  hippo_status st = make_tmap(&tmA, a.feats_bf16, a.n, a.d, kTcBM);
+  hippo_status st = make_tmap(&tmA, a.a_rows, a.a_total, a.d, kTcBM);
   if (st != HIPPO_OK) return st;
-  st = make_tmap(&tmB, a.feats_bf16, a.n, a.d, kTcBN / 2);
+  st = make_tmap(&tmB, a.b_rows, a.b_total, a.d, kTcBN / 2);
   if (st != HIPPO_OK) return st;
   TcParams p{};
-  p.n = a.n;
   p.kblocks = a.d / kTcBK;
-  p.bnorm = a.norm;
-  const int64_t nI = (a.n + kTcBN - 1) / kTcBN;
-  p.n_tiles = (int)nI;
-  const int64_t units = nI * (nI + 1) / 2;
-  if (units > 0x7fffffffll) { set_error("tc_mask_launch: n too large"); return HIPPO_E_BADARG; }
+  p.mask_rect = a.rect ? 1 : 0;
+  p.dyn_k = a.dyn_k;
+  p.na = a.na;
+  p.a_row0 = a.a_row0;
+  p.b_row0 = a.b_row0;
+  p.anorm = a.anorm;
+  p.bnorm = a.bnorm;
+  const int h = (a.na + kTcBN - 1) / kTcBN;
+  // the device-side prologue recomputes n / n_tiles / units (the rectangle's extent lives in device memory); the
+  // host values only bound the grid: the triangle's unit count, or the most the rectangle can have
+  p.n = a.na;
+  p.n_tiles = h;
+  const int64_t bt = (a.b_total + kTcBN - 1) / kTcBN;
+  const int64_t units = a.rect ? bt * h : (int64_t)h * (h + 1) / 2;
+  if (units > 0x7fffffffll) { set_error("tc_mask_launch: too many tiles"); return HIPPO_E_BADARG; }
   p.units = (int)units;
   p.gamma = a.gamma;
   p.band_exact = a.band_exact;
@@ -805,13 +812,12 @@ hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s) {
   p.inexact = a.inexact;
   p.mask = a.mask;
   p.words_per_row = a.words_per_row;
+  p.rowhit = a.rowhit;
   p.uncertain = a.uncertain;
   p.uncertain_count = a.uncertain_count;
   p.uncertain_cap = a.uncertain_cap;
-  p.dyn_k = a.dyn_k;
-  p.band_rows = a.band_rows;
   p.debug = debug_flags();
-  return launch<EPI_MASK>(tmA, tmB, p, s);
+  return launch<EPI_MASK>(tmA, tmB, p, s, a.max_pairs);
 }
 
 }  // namespace hippo

@@ -33,21 +33,34 @@ struct TcTopkArgs {
 int tc_topk_splits(int64_t n, int nq);
 hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s);
 
+// Similarity decisions of one band of rows (consolidate.cu).  A = rows [a_row0, a_row0 + na) of a_rows; a pair's bit
+// is !(sim < gamma); pairs too close to gamma for bf16 inputs go to the `uncertain` list instead.
+//   rect == false: B = the same band (b_rows = a_rows, b_row0 = a_row0): lower triangle, bit (i, j) for j < i into
+//                  the band-local bit matrix `mask`
+//   rect == true : B = rows [b_row0, b_row0 + *dyn_k) of b_rows (the rows kept so far), all columns below *dyn_k;
+//                  only the OR over a band row's bits is kept (`rowhit`)
 struct TcMaskArgs {
-  const void* feats_bf16;    // [n, d] bf16
-  const float* norm;         // [n]
-  int64_t n;
+  const void* a_rows;        // [a_total, d] bf16
+  int64_t a_total;
+  const void* b_rows;        // [b_total, d] bf16
+  int64_t b_total;
   int d;
+  bool rect;
+  int64_t a_row0, b_row0;
+  int na;                    // rows of the band
+  const float* anorm;        // [na] norms of the band's rows
+  const float* bnorm;        // norms of the B rows, bnorm[0] belongs to row b_row0
+  const int32_t* dyn_k;      // rectangle: device count of valid B rows
   float gamma;
   float band_exact, band_inexact;
   const int32_t* inexact;    // device flag from hippo_bank_build
-  uint32_t* mask;            // [n, words_per_row] bit j of row i: !(sim(i,j) < gamma), j < i
+  uint32_t* mask;            // triangle: band-local bit matrix (rows with 8 words per 256-column tile)
   int64_t words_per_row;
-  uint2* uncertain;          // (i, j) pairs within the band
+  int32_t* rowhit;           // rectangle: [na], zeroed by the caller; 1 = the band row conflicts with a kept row
+  uint2* uncertain;          // (band row, column) pairs within the band of gamma
   int32_t* uncertain_count;  // zero-initialised by the caller
   int32_t uncertain_cap;
-  const int32_t* dyn_k;      // banded mode (consolidate.cu): device count of final rows; null = whole triangle
-  int band_rows;             // rows of this band (A rows [*dyn_k, *dyn_k + band_rows))
+  int max_pairs;             // > 0: use at most this many CTA pairs (leave SMs to kernels running beside this one)
 };
 hippo_status tc_mask_launch(const TcMaskArgs& a, cudaStream_t s);
 
