@@ -27,6 +27,7 @@ SOURCES = [
     "topk_single.cu",
     "topk_batched.cu",
     "topk_rows.cu",
+    "topk_small.cu",
     "recall.cu",
     "exchange.cu",
     "sim_tc.cu",

@@ -200,20 +200,6 @@ __device__ __forceinline__ uint64_t list_kth(const uint64_t (&L)[kListRegs], int
   }
   return r;
 }
-// r[j] for a run-time j without local memory: a 5-level select tree over the 32 registers.
-__device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
-  uint32_t a[16], b[8], c[4], d[2];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
-  return (j & 16) ? d[1] : d[0];
-}
-
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100

@@ -13,6 +13,13 @@ hippo_status topk_few_launch(const void* bank, const float* norm, int64_t n, con
                              int64_t row_base, const uint64_t* after_key, uint64_t* part, int* nparts_out,
                              cudaStream_t s);
 
+// topk_small.cu: 3 .. 64 queries, bank rows on the M side of the MMA, deeper bank pipeline
+bool topk_small_supported(int d, int nq);
+int topk_small_grid(int64_t n);
+hippo_status topk_small_launch(const void* bank, const float* norm, int64_t n, int d, const void* qbf, const float* qnorm,
+                               int nq, int k, int64_t row_base, const uint64_t* after_key, uint64_t* part, uint32_t* gthr,
+                               int* nparts_out, cudaStream_t s);
+
 struct BatchedLayout {
   __nv_bfloat16* qbf;
   float* qnorm;
@@ -44,6 +51,10 @@ static BatchedLayout batched_layout(void* ws, size_t ws_bytes, int64_t n, int d,
   L.progress = L.thr_ord ? L.thr_ord + (size_t)nq * (1 + (size_t)k) : nullptr;
   size_t part_elems = (size_t)2 * L.splits * nq * k;
   if (topk_few_supported(d, nq) && topk_few_part_elems(nq, k) > part_elems) part_elems = topk_few_part_elems(nq, k);
+  if (topk_small_supported(d, nq)) {
+    const size_t need = (size_t)topk_small_grid(n) * nq * k;
+    if (need > part_elems) part_elems = need;
+  }
   L.part = c.take<uint64_t>(part_elems);
   L.bytes = c.used();
   return L;
@@ -79,6 +90,8 @@ static hippo_status batched_parts(const void* bank, const float* norm, int64_t n
   st = hippo_bank_build(q, HIPPO_F32, nq, d, d, L.qbf, L.qnorm, nullptr, stream);
   if (st != HIPPO_OK) return st;
   if (L.nq_pad > nq) HIPPO_CUDA(cudaMemsetAsync(L.qbf + (size_t)nq * d, 0, (size_t)(L.nq_pad - nq) * d * 2, s));
+  if (topk_small_supported(d, nq))   // 3 .. 64 queries: HBM bound, bank rows on the M side (topk_small.cu)
+    return topk_small_launch(bank, norm, n, d, L.qbf, L.qnorm, nq, k, row_base, after_key, L.part, L.thr_ord, nparts_out, s);
   TcTopkArgs a{};
   a.bank = bank;
   a.bnorm = norm;

@@ -112,24 +112,27 @@ def test_ragged_shapes_both_paths_agree_with_oracle(cuda_device, n, d, nq, k):
             assert np.all(idx[qi][kk:] == -1)
 
 
-@pytest.mark.parametrize("nq", [2, 3, 4, 5, 7, 8])
+@pytest.mark.parametrize("nq", [2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 64, 65])
 def test_few_queries_ride_one_bank_pass(cuda_device, nq):
     """A few queries of dimension 1024 behind the batched entry (two take the GEMV with two accumulators per row,
-    topk_single.cu; more go to the tensor cores): bit-equal to the single-query kernel on the lattice bank, within
-    the parity rule on Gaussian rows, NaN rows first, paging beyond HIPPO_TOPK_MAX, row counts off the 4-row groups."""
-    from hippomm_b200 import MemoryBank
+    topk_single.cu; 3 .. 64 the small-batch tcgen05 kernel with the bank rows on the M side, topk_small.cu; more the
+    256-query tiles of sim_tc.cu): bit-equal to the single-query kernel on the lattice bank, within the parity rule
+    on Gaussian rows, NaN rows first, paging beyond HIPPO_TOPK_MAX, row counts off the 4-row groups / 128-row tiles."""
+    from hippomm_b200 import MemoryBank, synth
 
     bank_h, queries, fam = cases.search_lattice_small()
+    if nq > len(queries):
+        queries, fam = synth.lattice_queries_np(4, nq, bank_h.shape[1], len(bank_h))
     bank = MemoryBank.from_rows(bank_h)
     bi, bs = _search(bank, queries[:nq], 10, "batched")
     for qi in range(nq):
         si, ss = _search(bank, queries[qi:qi + 1], 10, "single")
         assert np.array_equal(bi[qi], si[0]) and np.array_equal(bs[qi].view(np.uint32), ss[0].view(np.uint32))
     g = cases.golden()
-    for qi in range(nq):
+    for qi in range(min(nq, len(g["search_lat_idx"]))):
         check_topk_exact(bi[qi], bs[qi], g["search_lat_idx"][qi], g["search_lat_sim"][qi], what=f"few q{qi}")
     rng = np.random.default_rng(100 + nq)
-    for n in (1, 3, 1021):
+    for n in (1, 3, 1021, 40000):
         b = rng.standard_normal((n, 1024)).astype(np.float32)
         if n > 2:
             b[2] = 0.0                                        # zero-norm row: NaN, sorts first (vo:185)
