@@ -155,15 +155,19 @@ __device__ __forceinline__ float topk_filter_threshold(uint64_t kth_key, float a
 // hashed to it (fire-and-forget RED.MAX, no dependent round trips).  The k slots hold the scores of k
 // DISTINCT rows (different hash classes), so min(pool) is a valid lower bound on the final k-th best score,
 // under any interleaving.  It is published through thr_ord (RED.MAX, monotone), which only gates the
-// approximate filter (with slack): results do not depend on timing.  Returns the bound it published (0 = none).
-__device__ __forceinline__ uint32_t pool_update(uint32_t* pool_q, int k, uint32_t ord, uint32_t grow,
-                                                uint32_t* thr_ord_q) {
+// approximate filter (with slack): results do not depend on timing.
+__device__ __forceinline__ void pool_push(uint32_t* pool_q, int k, uint32_t ord, uint32_t grow) {
   const int slot = (int)(((uint64_t)(grow * 2654435761u) * (uint32_t)k) >> 32);
-  atomicMax(&pool_q[slot], ord);
+  atomicMax(&pool_q[slot], ord);                       // result unused: a fire-and-forget RED.MAX
+}
+// min over the k slots = a valid lower bound on the final k-th best score; published through thr_ord.  One L2 round
+// trip (the k loads are independent): done ONCE per chunk after all of the chunk's hits have been pushed -- a scene of
+// near-duplicate rows puts dozens of hits into one chunk, and a round trip per hit held the warp (and with it the
+// TMEM accumulator, and with that the MMA issuer) for ~700 cycles each.
+__device__ __forceinline__ uint32_t pool_min(const uint32_t* pool_q, int k, uint32_t* thr_ord_q) {
   uint32_t m = 0xffffffffu;
   for (int j = 0; j < k; ++j) {
-    uint32_t g = __ldcg(&pool_q[j]);
-    if (j == slot) g = g > ord ? g : ord;
+    const uint32_t g = __ldcg(&pool_q[j]);
     m = g < m ? g : m;
   }
   if (m != 0) atomicMax(thr_ord_q, m);
@@ -521,6 +525,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (force) hits = 0xffffffffu;
                 uint32_t gord = gthr;
                 uint32_t n_calls = 0;
+                bool pushed = false;
                 while (hits) {
                   const int j = __ffs(hits) - 1;
                   hits &= hits - 1;
@@ -538,12 +543,18 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     ++n_calls;
                     const uint32_t ord = (uint32_t)(key >> 32);
                     if (ord > gord && p.pool != nullptr) {
-                      const uint32_t m = pool_update(p.pool + (size_t)arow * p.k, p.k, ord, grow, &p.thr_ord[arow]);
-                      gord = m > gord ? m : gord;
+                      pool_push(p.pool + (size_t)arow * p.k, p.k, ord, grow);
+                      pushed = true;
                     }
                     const uint64_t g = (uint64_t)gord << 32;
                     thr = topk_filter_threshold(g > kth_key ? g : kth_key, an);
                   }
+                }
+                if (pushed) {
+                  const uint32_t m = pool_min(p.pool + (size_t)arow * p.k, p.k, &p.thr_ord[arow]);
+                  gord = m > gord ? m : gord;
+                  const uint64_t g = (uint64_t)gord << 32;
+                  thr = topk_filter_threshold(g > kth_key ? g : kth_key, an);
                 }
                 if (p.debug & 64) { atomicAdd(&p.counters[0], 1ull); atomicAdd(&p.counters[1], (unsigned long long)n_calls); }
               }
