@@ -137,6 +137,7 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 constexpr int kSsimThreads = 256;
 constexpr int kSsimWarps = kSsimThreads / 32;
 constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
+constexpr int kSsimLiveSmem = 8 * 1024;        // see frames_ssim_launch (live finalisation)
 constexpr int kSsimBandMin = 14;               // finest band height of a launch (frames_ssim_launch)
 constexpr int kSsimBand = 56;                  // window rows per band (6 halo rows per band: 11%; 112-row bands measured
                                                // slower on one stream-hour: fewer, longer warp items, longer tail)
@@ -168,6 +169,11 @@ struct SsimArgs {
   const int32_t* pair_a; const int32_t* pair_b;
   const int2* minmax; int range_mode, bh, nbands, nchunks;
   double* part_ssim; unsigned long long* part_sse;   // partials of the launch's items, [nitems]
+  // live finalisation (pattern.cu, null otherwise): the warp that delivers the LAST partial of a pair adds the pair's
+  // partials in the fixed order of ssim_finalize_kernel and stores the pair's SSIM / MSE -- one 8-byte store that a
+  // boundary chain running beside this kernel polls (segment.cu, follow mode); pair_done[p] counts the partials of
+  // pair p (zeroed by the caller), out_* are indexed by the pair's number in the stream
+  unsigned int* pair_done; double* out_ssim; double* out_mse;
 };
 
 // One (pair, band, chunk) item, by one warp; `item` numbers the items of ALL pairs (pair-major), `slot` is where its
@@ -322,6 +328,20 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   if (lane == 0) {
     A.part_ssim[slot] = acc;
     A.part_sse[slot] = sse;
+    if (A.pair_done != nullptr) {
+      const int nparts = nbands * nchunks;
+      __threadfence();                                    // the partial is visible before the count
+      if (atomicAdd(&A.pair_done[p], 1u) == (unsigned)(nparts - 1)) {
+        __threadfence();
+        const int64_t slot0 = slot - (item - (int64_t)p * nparts);
+        double a = 0.0; unsigned long long e = 0;
+        for (int b = 0; b < nparts; ++b) { a += __ldcg(A.part_ssim + slot0 + b); e += __ldcg(A.part_sse + slot0 + b); }
+        if (A.out_mse) A.out_mse[p] = (double)e / (65025.0 * (double)h * (double)w);
+        double v = __longlong_as_double(0x7ff8000000000000ll);
+        if (h >= 7 && w >= 7) v = a / ((double)(h - 6) * (double)(w - 6));
+        if (A.out_ssim) __stcg(A.out_ssim + p, v);
+      }
+    }
   }
 }
 
@@ -422,8 +442,12 @@ hippo_status frames_gray_launch(const uint8_t* frames, int nf, int h, int w, int
 // converted by frames_gray_launch into the same workspace.  Persistent warps (see ssim_pair_persistent_kernel);
 // `bh` window rows per band (a multiple of 7 up to kSsimBand: shorter bands = more, shorter items for the chunk that
 // ends the stream); `counter` is a zeroed uint32 nobody else uses (null: one warp per item, static).
+// `pair_done` (null, or nf - 1 zeroed counters): live finalisation -- no finalize launch, every pair's result is stored
+// by the warp that completes it (see SsimArgs); the launch then asks for kSsimLiveSmem bytes of (untouched) dynamic
+// shared memory, which keeps its CTAs off the SM the boundary chain reserved for itself (segment.cu, follow mode).
 hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes, int p0, int p1, int bh,
-                                unsigned int* counter, double* out_ssim, double* out_mse, cudaStream_t s) {
+                                unsigned int* counter, unsigned int* pair_done, double* out_ssim, double* out_mse,
+                                cudaStream_t s) {
   FrameLayout L = frame_layout(ws, ws_bytes, nf, h, w, nf - 1);
   if (p1 <= p0) return HIPPO_OK;
   HIPPO_REQUIRE(bh >= 1 && bh <= kSsimBand && kSsimBand % bh == 0, "frames_ssim_launch: band height %d", bh);
@@ -434,8 +458,13 @@ hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes,
   const int64_t nitems = (int64_t)(p1 - p0) * nparts;
   const int64_t part_off = (int64_t)p0 * L.nparts_max;
   const SsimArgs A{L.gray, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, bh, nbands, L.nchunks, L.part_ssim + part_off,
-                   L.part_sse + part_off};
+                   L.part_sse + part_off, pair_done, pair_done ? out_ssim : nullptr, pair_done ? out_mse : nullptr};
   int64_t grid = (nitems + kSsimWarps - 1) / kSsimWarps;
+  if (pair_done != nullptr) {
+    ssim_pair_kernel<4><<<(unsigned)grid, kSsimThreads, kSsimLiveSmem, s>>>(A, nitems, (int64_t)p0 * nparts);
+    HIPPO_CUDA(cudaGetLastError());
+    return HIPPO_OK;
+  }
   if (counter != nullptr) {
     const int64_t cap = (int64_t)sm_count() * 3;
     if (grid > cap) grid = cap;
@@ -497,7 +526,7 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   HIPPO_REQUIRE(npairs <= 65535, "hippo_frame_pairs: at most 65535 pairs per call");
   const int64_t nitems = (int64_t)npairs * L.nparts;
   const SsimArgs A{L.gray, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks, L.part_ssim,
-                   L.part_sse};
+                   L.part_sse, nullptr, nullptr, nullptr};
   ssim_pair_kernel<4><<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(A, nitems, 0);
   HIPPO_CUDA(cudaGetLastError());
   ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nparts, h, w,

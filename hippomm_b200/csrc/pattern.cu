@@ -20,35 +20,52 @@
 
 namespace hippo {
 
-// stream descriptor + fresh chain state; clears the item counters of the SSIM launches
+// stream descriptor + fresh chain state; clears the item counters of the SSIM launches; follow mode (pair_done != null):
+// clears the per-pair partial counts and marks every pair's SSIM as pending
 __global__ void pattern_init_kernel(hippo_stream_desc* desc, hippo_segment_state* state, hippo_stream_desc value,
-                                    unsigned int* counters, int ncounters) {
-  *desc = value;
-  state->current_start = 0.0;
-  state->hint = 0;
-  state->count = 0;
-  state->done = 0;
-  for (int i = 0; i < ncounters; ++i) counters[i] = 0;
+                                    unsigned int* counters, int ncounters, unsigned int* pair_done, double* ssim,
+                                    int npairs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (t == 0) {
+    *desc = value;
+    state->current_start = 0.0;
+    state->hint = 0;
+    state->count = 0;
+    state->done = 0;
+  }
+  for (int i = t; i < ncounters; i += nt) counters[i] = 0;
+  if (pair_done != nullptr)
+    for (int i = t; i < npairs; i += nt) { pair_done[i] = 0; ssim[i] = __longlong_as_double((long long)kSsimPending); }
 }
 
 hippo_status frames_gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
                                 cudaStream_t s);
 hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes, int p0, int p1, int bh,
-                                unsigned int* counter, double* out_ssim, double* out_mse, cudaStream_t s);
+                                unsigned int* counter, unsigned int* pair_done, double* out_ssim, double* out_mse,
+                                cudaStream_t s);
 hippo_status segment_resume_launch(const hippo_stream_desc* streams, int32_t nstreams, hippo_segment_state* states,
                                    int64_t frames_ready, int final_pass, double max_dur, double min_dur, double ssim_thr,
-                                   double db_thr, size_t smem_reserve, cudaStream_t s);
+                                   double db_thr, size_t smem_reserve, long long follow_ns, cudaStream_t s);
+int segment_stage_frames();
 constexpr int kPatternMaxChunks = 256;
 
 struct PatternLayout {
   void* lane_ws[2]; size_t lane_bytes;
   hippo_stream_desc* desc; hippo_segment_state* state;
   unsigned int* counters;
+  unsigned int* pair_done;
   size_t bytes;
 };
 
+static bool pattern_follow(int nf) {
+  const char* e = getenv("HIPPO_PATTERN_FOLLOW");     // 0: the chunk-by-chunk resumable chain of round 2's first version
+  return nf > 1 && nf <= segment_stage_frames() && !(e && atoi(e) == 0);
+}
+
 static int pattern_chunk(int nf, int chunk_pairs) {
-  int cp = chunk_pairs > 0 ? chunk_pairs : 444;     // 444 pairs = three SSIM CTAs per SM on 148 SMs (at 224 x 224)
+  // one wave of SSIM CTAs at 224 x 224 (8 items per pair, 8 warps per CTA): 444 pairs = three CTAs per SM on 148 SMs,
+  // 588 = four per SM on the 147 SMs the follow-mode chain leaves to them
+  int cp = chunk_pairs > 0 ? chunk_pairs : (pattern_follow(nf) ? 588 : 444);
   if (cp > nf - 1) cp = nf - 1;
   if (cp < 1) cp = 1;
   if ((nf - 1 + cp - 1) / cp > kPatternMaxChunks - 2) cp = (nf - 1 + kPatternMaxChunks - 3) / (kPatternMaxChunks - 2);
@@ -67,6 +84,7 @@ static PatternLayout pattern_layout(void* ws, size_t ws_bytes, int nf, int h, in
   L.desc = c.take<hippo_stream_desc>(1);
   L.state = c.take<hippo_segment_state>(1);
   L.counters = c.take<unsigned int>(kPatternMaxChunks);
+  L.pair_done = c.take<unsigned int>(nf > 1 ? nf - 1 : 1);
   L.bytes = c.used();
   return L;
 }
@@ -167,12 +185,26 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   d.out_bounds = out_bounds;
   d.out_count = out_count;
   d.max_segments = max_segments;
-  pattern_init_kernel<<<1, 1, 0, chain>>>(L.desc, L.state, d, L.counters, kPatternMaxChunks);
+  const bool follow = nchunks > 0 && pattern_follow(nfv);
+  pattern_init_kernel<<<follow ? 8 : 1, 256, 0, chain>>>(L.desc, L.state, d, L.counters, kPatternMaxChunks,
+                                                         follow ? L.pair_done : nullptr, out_ssim, nfv - 1);
   HIPPO_CUDA(cudaGetLastError());
   cudaEvent_t e_init = pooled_event(ev++);
   HIPPO_REQUIRE(e_init != nullptr, "hippo_pattern_separation: could not create events");
   HIPPO_CUDA(cudaEventRecord(e_init, chain));
   const size_t chain_smem = 0;
+  if (follow) {
+    // the chain, ONE launch that follows the SSIM kernels pair by pair from an SM of its own (segment.cu): 220 KB of
+    // dynamic shared memory leave no room for a gray (12 KB static) or SSIM (8 KB dynamic) CTA beside it.  A wait
+    // beyond the limit (HIPPO_FOLLOW_US, default 4 ms) suspends it; the final pass below picks up whatever is left.
+    const char* fe = getenv("HIPPO_FOLLOW_US");
+    const long long follow_ns = 1000ll * (fe && atoll(fe) > 0 ? atoll(fe) : 4000);
+    mark(chain, "follow begin", 0);
+    st = segment_resume_launch(L.desc, 1, L.state, 0, 0, max_segment_duration, min_segment_duration,
+                               frame_similarity_threshold, audio_silence_threshold, (size_t)220 * 1024, follow_ns, chain);
+    if (st != HIPPO_OK) return st;
+    mark(chain, "follow end", 0);
+  }
   // persistent SSIM warps (dynamic item queue) finish the SSIM phase sooner (444 vs 483 us per stream-hour) but crowd
   // the boundary chain, which then ends later: off unless HIPPO_SSIM_PERSISTENT=1
   const bool persistent = getenv("HIPPO_SSIM_PERSISTENT") && atoi(getenv("HIPPO_SSIM_PERSISTENT")) == 1;
@@ -200,25 +232,28 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
     // the chunks that end the stream use bands half as high: twice as many, shorter items, so the SMs run
     // dry within ~25 us of each other instead of ~50 (everything before is followed by more work anyway)
     const int bh = (nfv - 1 - p0 <= cp + cp / 2) ? fine_bh : 56;
-    st = frames_ssim_launch(nfv, h, w, L.lane_ws[0], L.lane_bytes, p0, p1, bh, persistent ? L.counters + i : nullptr,
-                            out_ssim, out_mse, s);
+    st = frames_ssim_launch(nfv, h, w, L.lane_ws[0], L.lane_bytes, p0, p1, bh,
+                            (persistent && !follow) ? L.counters + i : nullptr, follow ? L.pair_done : nullptr, out_ssim,
+                            out_mse, s);
     if (st != HIPPO_OK) return st;
     mark(s, "chunk end", i);
+    const bool last = i == nchunks - 1;
+    if (follow && i < nchunks - 2) continue;       // streams are in order: the last event of either lane covers the lane
     cudaEvent_t e = pooled_event(ev++);
     HIPPO_REQUIRE(e != nullptr, "hippo_pattern_separation: could not create events");
     HIPPO_CUDA(cudaEventRecord(e, s));
     HIPPO_CUDA(cudaStreamWaitEvent(chain, e, 0));
-    const bool last = i == nchunks - 1;
+    if (follow && !last) continue;                 // one final pass behind everything (a no-op when the chain got through)
     mark(chain, "chain begin", i);
     // pairs < p1 are final, i.e. frames < p1 + 1 are covered (every earlier chunk's event was waited for above)
     st = segment_resume_launch(L.desc, 1, L.state, p1 + 1, last ? 1 : 0, max_segment_duration, min_segment_duration,
-                               frame_similarity_threshold, audio_silence_threshold, chain_smem, chain);
+                               frame_similarity_threshold, audio_silence_threshold, chain_smem, 0, chain);
     if (st != HIPPO_OK) return st;
     mark(chain, "chain end", i);
   }
   if (nchunks == 0) {
     st = segment_resume_launch(L.desc, 1, L.state, nfv, 1, max_segment_duration, min_segment_duration,
-                               frame_similarity_threshold, audio_silence_threshold, 0, chain);
+                               frame_similarity_threshold, audio_silence_threshold, 0, 0, chain);
     if (st != HIPPO_OK) return st;
   }
   cudaEvent_t e_done = pooled_event(ev++);

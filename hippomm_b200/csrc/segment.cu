@@ -148,12 +148,21 @@ __device__ __forceinline__ int window_class(const double* __restrict__ e512, int
 // the final one only takes the segments whose window [current_start, current_end] is covered by the first
 // `frames_ready` frames (their adjacent-pair SSIMs are final) -- so the boundary chain of a stream can run under the
 // SSIM kernels of its later frames, one launch per chunk of frames, with no cross-kernel waiting anywhere.
+//
+// Follow mode (follow_ns > 0, pattern.cu): ONE launch that runs beside the SSIM kernels of the same stream, on an SM
+// of its own (the launch asks for most of an SM's shared memory and the SSIM CTAs for a few KB each, so they are never
+// placed together: the chain keeps its stand-alone speed instead of sharing issue slots).  The SSIM array starts out
+// filled with kSsimPending; a video thread whose pair is still pending polls the pair's 8-byte result (stored once by
+// the SSIM warp that completes the pair: the data is its own flag) and keeps the value in shared memory.  Only the
+// pairs the reference's scan would look at are ever waited for.  A wait longer than follow_ns -- the SSIM kernels are
+// not running beside this one: serialising profiler, sanitizer, launch-blocking debug runs -- suspends the chain
+// exactly like a gated pass; the final resumable pass the host always enqueues behind the SSIM kernels completes it.
 __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_stream_desc* __restrict__ streams,
                                                                  int nstreams, double max_dur, double min_dur,
                                                                  double ssim_thr, double db_thr,
                                                                  hippo_segment_state* __restrict__ states,
                                                                  int64_t frames_ready, int final_pass,
-                                                                 unsigned long long* dbg) {
+                                                                 long long follow_ns, unsigned long long* dbg) {
   extern __shared__ double s_stage[];          // [kStageFrames] frame times, [kStageFrames] ssim
   // per-segment results, triple-buffered so that ONE barrier per segment suffices: segment k uses set k % 3,
   // the last thread re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
@@ -161,6 +170,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   __shared__ long long s_lo[3];
   __shared__ int s_vpick[3];                   // latest pair below the threshold, as frame number - hint (-1 = none)
   __shared__ int s_apick[3], s_amb[3];         // earliest window known to be below the threshold / earliest undecided one
+  __shared__ int s_abort;                      // follow mode: a wait timed out
   const int tid = threadIdx.x;
   const int si = blockIdx.x;
   if (si >= nstreams) return;
@@ -171,6 +181,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   const bool has_audio = S.pcm != nullptr && S.sample_rate != 0.0;    // `audio_data is not None and audio_sample_rate`
   const double sr = S.sample_rate;
   const int64_t nf = S.nframes;
+  // follow mode needs the staged copy (the host only asks for it when the frames fit)
+  const bool follow = follow_ns > 0 && states != nullptr && has_video && nf <= kStageFrames;
 
   const double* ftimes = S.frame_times;
   const double* ssim = S.ssim;
@@ -187,13 +199,18 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     };
     stage(S.frame_times, s_stage, nf);
     ftimes = s_stage;
-    if (S.ssim != nullptr) {
+    if (S.ssim != nullptr && follow) {
+      // whatever is final by now; the rest stays kSsimPending and is polled by the thread that needs it
+      for (int64_t i = tid; i < nf - 1; i += kSegThreads) s_stage[kStageFrames + i] = ld_volatile_f64(S.ssim + i);
+      ssim = s_stage + kStageFrames;
+    } else if (S.ssim != nullptr) {
       const int64_t pairs = (states != nullptr && !final_pass) ? (frames_ready - 1 < nf - 1 ? frames_ready - 1 : nf - 1) : nf - 1;
       stage(S.ssim, s_stage + kStageFrames, pairs > 0 ? pairs : 0);
       ssim = s_stage + kStageFrames;
     }
   }
   if (tid < 3) { s_lo[tid] = -1; s_vpick[tid] = -1; s_apick[tid] = 0x7fffffff; s_amb[tid] = 0x7fffffff; }
+  if (tid == 0) s_abort = 0;
   __syncthreads();
 
   // hm:1027-1032
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   if (states != nullptr) { cs = states[si].current_start; hint = states[si].hint; count = states[si].count; }
   const int count0 = count;
   // a pass that is not final may only look at frames below frames_ready; it needs one of them BEYOND the window
-  const bool gated = states != nullptr && !final_pass && has_video;
+  const bool gated = states != nullptr && !final_pass && has_video && !follow;
   const double t_ready = (gated && frames_ready > 0) ? ftimes[(frames_ready < nf ? frames_ready : nf) - 1] : 0.0;
   long long t_pre = 0, t_bar = 0, t_tail = 0, n_exact = 0;
   while (cs < total) {                               // hm:1036
@@ -248,8 +265,21 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
             const double t = ftimes[i];
             const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
             if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
-            if (ssim != nullptr && i > hint && tp >= cs && t <= ce && ssim[i - 1] < ssim_thr)   // NaN compares false, as in Python
-              cand = (int)(i - hint);         // a run of more than 2^31 frames inside one window does not exist
+            if (ssim != nullptr && i > hint && tp >= cs && t <= ce) {
+              double sv = ssim[i - 1];
+              if (follow && __double_as_longlong(sv) == (long long)kSsimPending) {
+                // the pair's SSIM warp has not delivered yet: poll its result, keep it for the later segments
+                const unsigned long long t0 = globaltimer_ns();
+                for (;;) {
+                  sv = ld_volatile_f64(S.ssim + (i - 1));
+                  if (__double_as_longlong(sv) != (long long)kSsimPending) { s_stage[kStageFrames + i - 1] = sv; break; }
+                  if (globaltimer_ns() - t0 > (unsigned long long)follow_ns) { s_abort = 1; break; }
+                  __nanosleep(40);
+                }
+              }
+              if (sv < ssim_thr)              // NaN compares false, as in Python
+                cand = (int)(i - hint);       // a run of more than 2^31 frames inside one window does not exist
+            }
           }
           const int wmax = __reduce_max_sync(0xffffffffu, cand);             // one shared-memory atomic per warp
           if ((tid & 31) == 0 && wmax >= 0) atomicMax(&s_vpick[set], wmax);
@@ -273,6 +303,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
     const long long c2 = dbg ? clock64() : 0;
     __syncthreads();
     const long long c3 = dbg ? clock64() : 0;
+    if (follow && s_abort) { suspended = true; break; }   // nothing of this segment has been committed
 
     if (has_video) {
       const long long lo = s_lo[set];
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
 static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nstreams, double max_segment_duration,
                                    double min_segment_duration, double frame_similarity_threshold,
                                    double audio_silence_threshold, hippo_segment_state* states, int64_t frames_ready,
-                                   int final_pass, void* stream, size_t smem_reserve = 0) {
+                                   int final_pass, void* stream, size_t smem_reserve = 0, long long follow_ns = 0) {
   using namespace hippo;
   HIPPO_REQUIRE(nstreams >= 0, "hippo_segment_boundaries: nstreams < 0");
   if (nstreams == 0) return HIPPO_OK;
@@ -356,7 +387,7 @@ static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nst
   if (getenv("HIPPO_SEG_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
   segment_kernel<<<nstreams, kSegThreads, smem, (cudaStream_t)stream>>>(
       streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
-      audio_silence_threshold, states, frames_ready, final_pass, dbg);
+      audio_silence_threshold, states, frames_ready, final_pass, follow_ns, dbg);
   if (dbg) {
     unsigned long long h[8];
     cudaStreamSynchronize((cudaStream_t)stream);
@@ -372,10 +403,11 @@ static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nst
 namespace hippo {
 hippo_status segment_resume_launch(const hippo_stream_desc* streams, int32_t nstreams, hippo_segment_state* states,
                                    int64_t frames_ready, int final_pass, double max_dur, double min_dur, double ssim_thr,
-                                   double db_thr, size_t smem_reserve, cudaStream_t s) {
+                                   double db_thr, size_t smem_reserve, long long follow_ns, cudaStream_t s) {
   return launch_segment(streams, nstreams, max_dur, min_dur, ssim_thr, db_thr, states, frames_ready, final_pass, (void*)s,
-                        smem_reserve);
+                        smem_reserve, follow_ns);
 }
+int segment_stage_frames() { return kStageFrames; }
 }  // namespace hippo
 
 extern "C" hippo_status hippo_segment_boundaries(const hippo_stream_desc* streams, int32_t nstreams,

@@ -437,9 +437,11 @@ def _issue_streams(dev: torch.device, n: int):
 
 
 def _side_streams(dev: torch.device, n: int):
+    # triples (lane, lane, chain) for hippo_pattern_separation: the chain stream is a high-priority stream, so its one
+    # small CTA is placed ahead of the thousands of pending SSIM CTAs when an SM frees up
     pool = _side.setdefault(dev.index, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
+        pool.append(torch.cuda.Stream(device=dev, priority=-1 if len(pool) % 3 == 2 else 0))
     return pool[:n]
 
 

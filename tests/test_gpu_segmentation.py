@@ -315,3 +315,55 @@ def test_overlapped_pipeline_equals_stage_by_stage(cuda_device, chunk_pairs):
     bv, cv, _ = pattern_separation_device(fd, ft, None, None, 30.0, 10.0, 0.95, -40.0, 256, chunk_pairs=chunk_pairs)
     wv = O.segment_boundaries(O.adjacent_ssim(frames), list(times), None, None)
     assert [tuple(x) for x in bv[: int(cv.item())].cpu().numpy().tolist()] == [tuple(w) for w in wv]
+
+
+@pytest.mark.parametrize("env", [{"HIPPO_FOLLOW_US": "1"}, {"HIPPO_FOLLOW_US": "30"}, {"HIPPO_PATTERN_FOLLOW": "0"}])
+def test_follow_mode_chain_suspends_and_completes(cuda_device, env, monkeypatch):
+    """The boundary chain that FOLLOWS the SSIM kernels pair by pair (segment.cu follow mode) gives up when a pair does
+    not arrive within its limit -- a serialising profiler, a launch-blocking debug run -- and the final resumable pass
+    finishes the stream: with a 1 us / 30 us limit most calls take that path at some segment, and the boundaries, the
+    SSIM values and the count must still be those of the stage-by-stage calls.  HIPPO_PATTERN_FOLLOW=0 is the
+    chunk-by-chunk chain (also what streams longer than the staged 6,000 frames use)."""
+    from hippomm_b200 import synth
+    from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device, pattern_separation_device,
+                                           segment_boundaries_device)
+
+    nsec, sr = 900, 8000
+    frames, _ = synth.frame_stream(41, nsec, 96, 80, min_scene=5, max_scene=40)
+    pcm = synth.audio_stream_int16(42, nsec * sr)
+    fd = torch.from_numpy(frames).to(cuda_device)
+    pd = torch.from_numpy(pcm.reshape(-1, 1)).to(cuda_device)
+    ft = torch.arange(nsec, dtype=torch.float64, device=cuda_device)
+    ssim, _ = frame_pair_scores_device(fd, range_mode=0)
+    pyr = audio_energy_device(pd)
+    b0, c0 = segment_boundaries_device(ssim, ft, pd, pyr, sr, 30.0, 10.0, 0.95, -40.0, 256)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for chunk_pairs in (0, 100):
+        for _ in range(3):
+            b1, c1, s1 = pattern_separation_device(fd, ft, pd, sr, 30.0, 10.0, 0.95, -40.0, 256, chunk_pairs=chunk_pairs)
+            torch.cuda.synchronize()
+            n = int(c0.item())
+            assert n > 20 and int(c1.item()) == n
+            assert torch.equal(b0[:n], b1[:n]) and torch.equal(s1, ssim)
+
+
+def test_stream_longer_than_the_staged_frames(cuda_device):
+    """More than 6,000 frames: the chain cannot stage the stream in shared memory, so the pipeline falls back to the
+    chunk-by-chunk resumable chain reading global memory; results as stage by stage."""
+    from hippomm_b200.segmentation import (frame_pair_scores_device, pattern_separation_device,
+                                           segment_boundaries_device)
+
+    g = torch.Generator(device="cpu").manual_seed(7)
+    nf = 6500
+    scene = torch.randint(0, 255, (nf // 25 + 1, 16, 16, 3), generator=g, dtype=torch.uint8)
+    frames = scene.repeat_interleave(25, dim=0)[:nf].clone()
+    frames[:, 0, 0, 0] = torch.arange(nf, dtype=torch.int64).remainder(7).to(torch.uint8)
+    fd = frames.to(cuda_device)
+    ft = torch.arange(nf, dtype=torch.float64, device=cuda_device)
+    ssim, _ = frame_pair_scores_device(fd, range_mode=0)
+    b0, c0 = segment_boundaries_device(ssim, ft, None, None, None, 30.0, 10.0, 0.95, -40.0, 1024)
+    b1, c1, s1 = pattern_separation_device(fd, ft, None, None, 30.0, 10.0, 0.95, -40.0, 1024)
+    torch.cuda.synchronize()
+    n = int(c0.item())
+    assert n > 200 and int(c1.item()) == n and torch.equal(b0[:n], b1[:n]) and torch.equal(s1, ssim)
