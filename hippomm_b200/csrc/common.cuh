@@ -154,6 +154,14 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -21,6 +21,7 @@
 //                        prefixes.  Issue-bound (integer ALU), not HBM-bound: see DESIGN.md.
 //   ssim_finalize_kernel: ordered sum of the warp partials -> mean SSIM, MSE
 #include "common.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 namespace hippo {
@@ -35,8 +36,32 @@ __device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r)
 // (frame, 512-pixel slice) items.  A warp takes 32 groups of 16 pixels per item = 1536 contiguous BGR bytes,
 // loaded as three fully coalesced 512-byte rows into the warp's shared-memory slot, then every lane picks up
 // its own 48 bytes (conflict-free: 12-word stride) and stores 16 gray bytes, coalesced.
+// One lane's 16 pixels of a staged warp item (48 BGR bytes at s[3 * lane ..]) -> 16 gray bytes, running min / max.
+__device__ __forceinline__ uint4 gray16(const uint4* s, int lane, uint32_t& lo, uint32_t& hi) {
+  const uint4 a = s[3 * lane], b = s[3 * lane + 1], c = s[3 * lane + 2];
+  const uint32_t w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
+  uint32_t out[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      // the pixel's B, G, R bytes into one register (one PRMT across two words), then two 16 x 8-bit dot
+      // products: 3735 B + 19235 G + 16384, + 9798 R
+      const int byte0 = (o * 4 + px) * 3;
+      const uint32_t bgr = __byte_perm(w[byte0 >> 2], w[(byte0 >> 2) + 1], 0x3210 + 0x1111 * (byte0 & 3));
+      const uint32_t y = (uint32_t)__dp2a_hi(kGrayW_R, bgr, __dp2a_lo(kGrayW_BG, bgr, 16384u)) >> 15;
+      lo = min(lo, y); hi = max(hi, y);
+      packed |= y << (px * 8);
+    }
+    out[o] = packed;
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// `gstride`: bytes from one gray frame to the next (a multiple of 128: no cache line holds bytes of two frames).
 __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __restrict__ frames, int64_t npix,
-                                                              int nf, uint8_t* __restrict__ gray,
+                                                              int nf, uint8_t* __restrict__ gray, int64_t gstride,
                                                               int2* __restrict__ minmax) {
   __shared__ uint4 s_stage[8][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -46,7 +71,7 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
   for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < nitems; item += (int64_t)gridDim.x * 8) {
     const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;
     const uint8_t* src = frames + f * npix * 3;
-    uint8_t* dst = gray + f * npix;
+    uint8_t* dst = gray + f * gstride;
     const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
     const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
     const uint4* p = reinterpret_cast<const uint4*>(src + g0 * 48);
@@ -57,27 +82,7 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
     __syncwarp();
     uint32_t lo = 255, hi = 0;
-    if (lane < left) {
-      const uint4 a = s_stage[warp][3 * lane], b = s_stage[warp][3 * lane + 1], c = s_stage[warp][3 * lane + 2];
-      const uint32_t w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
-      uint32_t out[4];
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        uint32_t packed = 0;
-#pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          // the pixel's B, G, R bytes into one register (one PRMT across two words), then two 16 x 8-bit dot
-          // products: 3735 B + 19235 G + 16384, + 9798 R
-          const int byte0 = (o * 4 + px) * 3;
-          const uint32_t bgr = __byte_perm(w[byte0 >> 2], w[(byte0 >> 2) + 1], 0x3210 + 0x1111 * (byte0 & 3));
-          const uint32_t y = (uint32_t)__dp2a_hi(kGrayW_R, bgr, __dp2a_lo(kGrayW_BG, bgr, 16384u)) >> 15;
-          lo = min(lo, y); hi = max(hi, y);
-          packed |= y << (px * 8);
-        }
-        out[o] = packed;
-      }
-      *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
-    }
+    if (lane < left) *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = gray16(s_stage[warp], lane, lo, hi);
     __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -94,13 +99,13 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
 // General path (1 channel, odd sizes, padded rows): grid (blocks_per_frame, nf), one byte per thread and step.
 __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restrict__ frames, int64_t npix,
                                                           int w, int pitch, int ch, uint8_t* __restrict__ gray,
-                                                          int2* __restrict__ minmax) {
+                                                          int64_t gstride, int2* __restrict__ minmax) {
   __shared__ uint32_t s_lo[8], s_hi[8];
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint8_t* src = frames + (int64_t)f * npix * ch;
   const int64_t gpix = npix / w * pitch;      // bytes of one padded gray frame
-  uint8_t* dst = gray + (int64_t)f * gpix;
+  uint8_t* dst = gray + (int64_t)f * gstride;
   uint32_t lo = 255, hi = 0;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < gpix;
        o += (int64_t)gridDim.x * blockDim.x) {
@@ -137,8 +142,7 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 constexpr int kSsimThreads = 256;
 constexpr int kSsimWarps = kSsimThreads / 32;
 constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
-constexpr int kSsimLiveSmem = 8 * 1024;        // see frames_ssim_launch (live finalisation)
-constexpr int kSsimBandMin = 14;               // finest band height of a launch (frames_ssim_launch)
+constexpr int kSsimLiveSmem = 8 * 1024;        // see frames_adjacent_live_launch
 constexpr int kSsimBand = 56;                  // window rows per band (6 halo rows per band: 11%; 112-row bands measured
                                                // slower on one stream-hour: fewer, longer warp items, longer tail)
 
@@ -165,7 +169,7 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_p
 // squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
 // [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
 struct SsimArgs {
-  const uint8_t* gray; int h, w, pitch;
+  const uint8_t* gray; int64_t gstride; int h, w, pitch;
   const int32_t* pair_a; const int32_t* pair_b;
   const int2* minmax; int range_mode, bh, nbands, nchunks;
   double* part_ssim; unsigned long long* part_sse;   // partials of the launch's items, [nitems]
@@ -190,7 +194,7 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   const int p = (int)(item / ((int64_t)nchunks * nbands));
   const int fa = pair_a ? pair_a[p] : p + 1;
   const int fb = pair_b ? pair_b[p] : p;
-  const int64_t gpix = (int64_t)h * pitch;
+  const int64_t gpix = A.gstride;
   const int wordx = (chunk * 30 + lane) * 4;                 // byte offset of this lane's word in a row
   const bool col_ok = wordx < pitch;
   const uint8_t* ga = gray + (int64_t)fa * gpix + wordx;
@@ -345,32 +349,12 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   }
 }
 
-// three CTAs per SM (at most 80 registers); four at 64 registers measured 3% slower
-// Static form: warp i of the grid takes item item0 + i.
-// kCtas = 4 (64 registers, no spill) is 6% faster when the kernel has the machine to itself (hippo_frame_pairs);
-// kCtas = 3 leaves more issue slots to a boundary chain running beside it (pattern.cu), which matters more there.
-template <int kCtas>
-__global__ void __launch_bounds__(kSsimThreads, kCtas) ssim_pair_kernel(const SsimArgs A, int64_t nitems, int64_t item0) {
+// One warp per item: warp i of the grid takes item item0 + i (explicit pair lists: pre-filter chain, QA de-dup).
+// Four CTAs per SM (64 registers, no spill).
+__global__ void __launch_bounds__(kSsimThreads, 4) ssim_pair_kernel(const SsimArgs A, int64_t nitems, int64_t item0) {
   const int64_t i = (int64_t)blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
   if (i >= nitems) return;
   ssim_item(A, item0 + i, i, threadIdx.x & 31);
-}
-
-// Persistent form (pattern.cu): every warp keeps taking the next item off a counter until none is left, so the
-// launch ends within one item of its work running out instead of rounding up to whole waves of CTAs, and consecutive
-// launches on different streams hand the SMs over warp by warp.
-// (Tried and dropped: CTAs leaving one SM free for the boundary chain -- with two launches in flight the second
-// launch's CTAs drain through the vacated slots without doing any work.)
-__global__ void __launch_bounds__(kSsimThreads, 3) ssim_pair_persistent_kernel(const SsimArgs A, int64_t nitems, int64_t item0,
-                                                                               unsigned int* __restrict__ counter) {
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    unsigned int i = 0;
-    if (lane == 0) i = atomicAdd(counter, 1u);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if ((int64_t)i >= nitems) break;
-    ssim_item(A, item0 + i, i, lane);
-  }
 }
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
@@ -389,92 +373,62 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
 
 struct FrameLayout {
   uint8_t* gray; int2* minmax; double* part_ssim; unsigned long long* part_sse;
-  int pitch, bh, nbands, nchunks, nparts, nparts_max; size_t bytes;
+  int pitch, bh, nbands, nchunks, nparts; int64_t gstride; size_t bytes;
 };
 static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int npairs) {
   Carver c(ws, ws_bytes);
   FrameLayout L{};
   L.pitch = (w + 3) & ~3;
-  L.gray = c.take<uint8_t>((size_t)nf * h * L.pitch);
+  L.gstride = (int64_t)align_up((size_t)h * L.pitch, 128);
+  L.gray = c.take<uint8_t>((size_t)nf * L.gstride);
   L.minmax = c.take<int2>((size_t)nf);
   const int out_rows = h >= 7 ? h - 6 : 0, out_cols = w >= 7 ? w - 6 : 0;
   L.bh = kSsimBand;
   L.nbands = out_rows > 0 ? (out_rows + L.bh - 1) / L.bh : 1;
   L.nchunks = out_cols > 0 ? (out_cols + kSsimChunk - 1) / kSsimChunk : 1;
   L.nparts = L.nbands * L.nchunks;
-  // room for the finest band height a launch may ask for (kSsimBandMin rows): frames_ssim_launch
-  const int nbands_fine = out_rows > 0 ? (out_rows + kSsimBandMin - 1) / kSsimBandMin : 1;
-  L.nparts_max = nbands_fine * L.nchunks;
-  L.part_ssim = c.take<double>((size_t)npairs * L.nparts_max);
-  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts_max);
+  L.part_ssim = c.take<double>((size_t)npairs * L.nparts);
+  L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts);
   L.bytes = c.used();
   return L;
 }
 
-// ---- the two halves of hippo_frame_pairs for adjacent pairs, separately launchable (pattern.cu): the gray
-// conversion of ALL frames once, then the SSIM of any range of adjacent pairs on any stream ----
-hippo_status frames_gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
-                                cudaStream_t s) {
-  FrameLayout L = frame_layout(ws, ws_bytes, nf, h, w, nf - 1);
-  if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
-    set_error("frames_gray_launch: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
-    return HIPPO_E_WORKSPACE;
-  }
-  HIPPO_REQUIRE(nf <= 65535, "hippo_frame_pairs: at most 65535 frames per call");
+// gray conversion of all frames (+ min / max), stream s
+static void gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, const FrameLayout& L, cudaStream_t s) {
   const int64_t npix = (int64_t)h * w;
   minmax_init_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.minmax, nf);
   int bpf = (int)((npix / 16 + 255) / 256);
   if (bpf < 1) bpf = 1;
   if (bpf > 64) bpf = 64;
-  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;
+  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
   if (vec) {
     const int64_t items = (npix / 16 + 31) / 32 * nf;
     const int64_t want = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
-    gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.minmax);
+    gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.gstride, L.minmax);
   } else {
-    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
+    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.gstride, L.minmax);
   }
-  HIPPO_CUDA(cudaGetLastError());
-  return HIPPO_OK;
 }
 
-// SSIM (data range from the first frame of each pair, hm:990) + MSE of adjacent pairs [p0, p1) of the nf frames
-// converted by frames_gray_launch into the same workspace.  Persistent warps (see ssim_pair_persistent_kernel);
-// `bh` window rows per band (a multiple of 7 up to kSsimBand: shorter bands = more, shorter items for the chunk that
-// ends the stream); `counter` is a zeroed uint32 nobody else uses (null: one warp per item, static).
-// `pair_done` (null, or nf - 1 zeroed counters): live finalisation -- no finalize launch, every pair's result is stored
-// by the warp that completes it (see SsimArgs); the launch then asks for kSsimLiveSmem bytes of (untouched) dynamic
-// shared memory, which keeps its CTAs off the SM the boundary chain reserved for itself (segment.cu, follow mode).
-hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes, int p0, int p1, int bh,
-                                unsigned int* counter, unsigned int* pair_done, double* out_ssim, double* out_mse,
-                                cudaStream_t s) {
+// Adjacent pairs [0, nf - 1) of a stream with LIVE finalisation (pattern.cu): gray conversion, then one SSIM launch
+// whose warps store every pair's result as they complete it (`pair_done`: nf - 1 zeroed counters, see SsimArgs) -- no
+// finalize launch.  The SSIM CTAs ask for kSsimLiveSmem bytes of (untouched) dynamic shared memory, the gray CTAs hold
+// 12 KB of static shared memory: neither fits on the SM the boundary chain reserved for itself (segment.cu, follow mode).
+hippo_status frames_adjacent_live_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
+                                         unsigned int* pair_done, double* out_ssim, double* out_mse, cudaStream_t s) {
   FrameLayout L = frame_layout(ws, ws_bytes, nf, h, w, nf - 1);
-  if (p1 <= p0) return HIPPO_OK;
-  HIPPO_REQUIRE(bh >= 1 && bh <= kSsimBand && kSsimBand % bh == 0, "frames_ssim_launch: band height %d", bh);
-  const int out_rows = h >= 7 ? h - 6 : 0;
-  const int nbands = out_rows > 0 ? (out_rows + bh - 1) / bh : 1;
-  const int nparts = nbands * L.nchunks;          // <= the layout's nparts * (kSsimBand / bh)
-  // the layout reserves nparts(kSsimBand) slots per pair; finer bands need more: frame_layout_fine below sizes for it
-  const int64_t nitems = (int64_t)(p1 - p0) * nparts;
-  const int64_t part_off = (int64_t)p0 * L.nparts_max;
-  const SsimArgs A{L.gray, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, bh, nbands, L.nchunks, L.part_ssim + part_off,
-                   L.part_sse + part_off, pair_done, pair_done ? out_ssim : nullptr, pair_done ? out_mse : nullptr};
-  int64_t grid = (nitems + kSsimWarps - 1) / kSsimWarps;
-  if (pair_done != nullptr) {
-    ssim_pair_kernel<4><<<(unsigned)grid, kSsimThreads, kSsimLiveSmem, s>>>(A, nitems, (int64_t)p0 * nparts);
-    HIPPO_CUDA(cudaGetLastError());
-    return HIPPO_OK;
+  if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
+    set_error("hippo_pattern_separation: frame workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
+    return HIPPO_E_WORKSPACE;
   }
-  if (counter != nullptr) {
-    const int64_t cap = (int64_t)sm_count() * 3;
-    if (grid > cap) grid = cap;
-    ssim_pair_persistent_kernel<<<(unsigned)grid, kSsimThreads, 0, s>>>(A, nitems, (int64_t)p0 * nparts, counter);
-  } else {
-    ssim_pair_kernel<3><<<(unsigned)grid, kSsimThreads, 0, s>>>(A, nitems, (int64_t)p0 * nparts);
-  }
+  const int npairs = nf - 1;
+  if (npairs <= 0) return HIPPO_OK;
+  gray_launch(frames, nf, h, w, ch, L, s);
   HIPPO_CUDA(cudaGetLastError());
-  ssim_finalize_kernel<<<(p1 - p0 + 127) / 128, 128, 0, s>>>(L.part_ssim + part_off, L.part_sse + part_off, p1 - p0, nparts, h, w,
-                                                           out_ssim + p0, out_mse ? out_mse + p0 : nullptr);
+  const int64_t nitems = (int64_t)npairs * L.nparts;
+  const SsimArgs A{L.gray, L.gstride, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, L.bh, L.nbands, L.nchunks,
+                   L.part_ssim, L.part_sse, pair_done, out_ssim, out_mse};
+  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, kSsimLiveSmem, s>>>(A, nitems, 0);
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
@@ -500,6 +454,7 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   HIPPO_REQUIRE(pair_a != nullptr || npairs == nf - 1, "hippo_frame_pairs: adjacent mode needs npairs == nf-1");
   if (npairs == 0) return HIPPO_OK;
   HIPPO_REQUIRE(frames != nullptr, "hippo_frame_pairs: null frames");
+  HIPPO_REQUIRE(nf <= 65535 && npairs <= 65535, "hippo_frame_pairs: at most 65535 frames / pairs per call");
   hippo_status st = check_arch();
   if (st != HIPPO_OK) return st;
   cudaStream_t s = (cudaStream_t)stream;
@@ -508,26 +463,12 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
     set_error("hippo_frame_pairs: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;
   }
-  const int64_t npix = (int64_t)h * w;
-  minmax_init_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.minmax, nf);
-  int bpf = (int)((npix / 16 + 255) / 256);
-  if (bpf < 1) bpf = 1;
-  if (bpf > 64) bpf = 64;
-  HIPPO_REQUIRE(nf <= 65535, "hippo_frame_pairs: at most 65535 frames per call");
-  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
-  if (vec) {
-    const int64_t items = (npix / 16 + 31) / 32 * nf;
-    const int64_t want = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
-    gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.minmax);
-  } else {
-    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.minmax);
-  }
+  gray_launch(frames, nf, h, w, ch, L, s);
   HIPPO_CUDA(cudaGetLastError());
-  HIPPO_REQUIRE(npairs <= 65535, "hippo_frame_pairs: at most 65535 pairs per call");
   const int64_t nitems = (int64_t)npairs * L.nparts;
-  const SsimArgs A{L.gray, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks, L.part_ssim,
-                   L.part_sse, nullptr, nullptr, nullptr};
-  ssim_pair_kernel<4><<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(A, nitems, 0);
+  const SsimArgs A{L.gray, L.gstride, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks,
+                   L.part_ssim, L.part_sse, nullptr, nullptr, nullptr};
+  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(A, nitems, 0);
   HIPPO_CUDA(cudaGetLastError());
   ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nparts, h, w,
                                                            out_ssim, out_mse);

@@ -3,16 +3,16 @@
 //
 // The stages have different bounds -- BGR -> gray is HBM bound, SSIM is integer-issue bound, the audio pyramid is HBM
 // bound and tiny, the boundary state machine is one sequential latency chain -- so run back to back they leave most
-// of the machine idle most of the time (0.82 ms per stream-hour, 0.12 of the HBM roofline).  Here the frames are
-// taken in chunks of `chunk_pairs` adjacent pairs:
-//   side stream A / B (alternating)   gray + SSIM of chunk i: the gray conversion of chunk i + 1 runs under the SSIM
-//                                     kernel of chunk i;
-//   side stream C                     audio pyramid first, then the boundary state machine in its RESUMABLE form
-//                                     (segment.cu): after every second chunk it takes the segments whose window is
-//                                     covered by finished SSIM values and suspends, so the chain runs under the SSIM
-//                                     kernels of the later chunks and only its last few segments remain at the end.
-// Ordering is by stream events only -- no kernel ever waits for another kernel -- and the launches come from this
-// host function (a Python loop over the chunks costs more host time than the kernels take).
+// of the machine idle most of the time (0.82 ms per stream-hour, 0.12 of the HBM roofline).  Here:
+//   side stream 2   the boundary state machine in FOLLOW mode (segment.cu), launched FIRST: one CTA on an SM of its
+//                   own that polls the SSIM values it needs as they are delivered, so the chain ends a few
+//                   microseconds after the last pair; then a final resumable pass behind everything, which completes
+//                   the chain if the follower gave up (it never waits longer than its limit, so a serialising
+//                   profiler or a launch-blocking debug run only costs that limit);
+//   side stream 1   audio pyramid (+ a flag the follower's gate polls);
+//   side stream 0   gray conversion, then the SSIM of all adjacent pairs as one launch, every pair's result stored by
+//                   the warp that completes it (frames.cu, live finalisation).
+// The launches come from this host function (a Python loop costs more host time than the kernels take).
 #include "common.cuh"
 
 #include <cstdlib>
@@ -20,11 +20,10 @@
 
 namespace hippo {
 
-// stream descriptor + fresh chain state; clears the item counters of the SSIM launches; follow mode (pair_done != null):
-// clears the per-pair partial counts and marks every pair's SSIM as pending
+// stream descriptor + fresh chain state; follow mode (pair_done != null): clears the per-pair partial counts and
+// marks every pair's SSIM as pending
 __global__ void pattern_init_kernel(hippo_stream_desc* desc, hippo_segment_state* state, hippo_stream_desc value,
-                                    unsigned int* counters, int ncounters, unsigned int* pair_done, double* ssim,
-                                    int npairs) {
+                                    unsigned int* pair_done, double* ssim, int npairs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   if (t == 0) {
     *desc = value;
@@ -33,58 +32,48 @@ __global__ void pattern_init_kernel(hippo_stream_desc* desc, hippo_segment_state
     state->count = 0;
     state->done = 0;
   }
-  for (int i = t; i < ncounters; i += nt) counters[i] = 0;
-  if (pair_done != nullptr)
+  if (pair_done != nullptr) {
     for (int i = t; i < npairs; i += nt) { pair_done[i] = 0; ssim[i] = __longlong_as_double((long long)kSsimPending); }
+    if (t == 0) { pair_done[npairs] = 0; pair_done[npairs + 1] = 0; }
+  }
 }
 
-hippo_status frames_gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
-                                cudaStream_t s);
-hippo_status frames_ssim_launch(int nf, int h, int w, void* ws, size_t ws_bytes, int p0, int p1, int bh,
-                                unsigned int* counter, unsigned int* pair_done, double* out_ssim, double* out_mse,
-                                cudaStream_t s);
+__global__ void pattern_flag_kernel(unsigned int* flag) { __threadfence(); *flag = 1u; }
+// holds a stream back until the follower is resident (or `limit_ns` have passed: it may be running AFTER us under a
+// serialising tool)
+__global__ void pattern_wait_kernel(const unsigned int* flag, long long limit_ns) {
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_volatile_u32(flag) == 0 && globaltimer_ns() - t0 < (unsigned long long)limit_ns) __nanosleep(100);
+}
+
+hippo_status frames_adjacent_live_launch(const uint8_t* frames, int nf, int h, int w, int ch, void* ws, size_t ws_bytes,
+                                         unsigned int* pair_done, double* out_ssim, double* out_mse, cudaStream_t s);
 hippo_status segment_resume_launch(const hippo_stream_desc* streams, int32_t nstreams, hippo_segment_state* states,
                                    int64_t frames_ready, int final_pass, double max_dur, double min_dur, double ssim_thr,
-                                   double db_thr, size_t smem_reserve, long long follow_ns, cudaStream_t s);
+                                   double db_thr, size_t smem_reserve, long long follow_ns,
+                                   const unsigned int* follow_gate, cudaStream_t s);
 int segment_stage_frames();
-constexpr int kPatternMaxChunks = 256;
-
 struct PatternLayout {
-  void* lane_ws[2]; size_t lane_bytes;
+  void* frame_ws; size_t frame_bytes;
   hippo_stream_desc* desc; hippo_segment_state* state;
-  unsigned int* counters;
-  unsigned int* pair_done;
+  unsigned int* pair_done;                    // [npairs] partials delivered per pair, then "audio pyramid complete", "follower resident"
   size_t bytes;
 };
 
-static bool pattern_follow(int nf) {
-  const char* e = getenv("HIPPO_PATTERN_FOLLOW");     // 0: the chunk-by-chunk resumable chain of round 2's first version
-  return nf > 1 && nf <= segment_stage_frames() && !(e && atoi(e) == 0);
+static bool pattern_follow() {
+  const char* e = getenv("HIPPO_PATTERN_FOLLOW");     // 0: no follower, the final pass runs the whole chain (A/B, debugging)
+  return !(e && atoi(e) == 0);
 }
 
-static int pattern_chunk(int nf, int chunk_pairs) {
-  // one wave of SSIM CTAs at 224 x 224 (8 items per pair, 8 warps per CTA): 444 pairs = three CTAs per SM on 148 SMs,
-  // 588 = four per SM on the 147 SMs the follow-mode chain leaves to them
-  int cp = chunk_pairs > 0 ? chunk_pairs : (pattern_follow(nf) ? 588 : 444);
-  if (cp > nf - 1) cp = nf - 1;
-  if (cp < 1) cp = 1;
-  if ((nf - 1 + cp - 1) / cp > kPatternMaxChunks - 2) cp = (nf - 1 + kPatternMaxChunks - 3) / (kPatternMaxChunks - 2);
-  return cp;
-}
-
-static PatternLayout pattern_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int chunk_pairs) {
+static PatternLayout pattern_layout(void* ws, size_t ws_bytes, int nf, int h, int w) {
   Carver c(ws, ws_bytes);
   PatternLayout L{};
-  const int cp = pattern_chunk(nf, chunk_pairs);
-  (void)cp;
   // one frame-pair workspace for the whole stream: gray image of every frame, per-pair partial sums
-  L.lane_bytes = nf > 1 ? align_up(hippo_frame_pairs_workspace_bytes(nf, h, w, nf - 1), 256) : 256;
-  L.lane_ws[0] = c.take<unsigned char>(L.lane_bytes);
-  L.lane_ws[1] = nullptr;
+  L.frame_bytes = nf > 1 ? align_up(hippo_frame_pairs_workspace_bytes(nf, h, w, nf - 1), 256) : 256;
+  L.frame_ws = c.take<unsigned char>(L.frame_bytes);
   L.desc = c.take<hippo_stream_desc>(1);
   L.state = c.take<hippo_segment_state>(1);
-  L.counters = c.take<unsigned int>(kPatternMaxChunks);
-  L.pair_done = c.take<unsigned int>(nf > 1 ? nf - 1 : 1);
+  L.pair_done = c.take<unsigned int>((nf > 1 ? nf - 1 : 0) + 2);
   L.bytes = c.used();
   return L;
 }
@@ -105,8 +94,9 @@ static cudaEvent_t pooled_event(size_t i) {
 extern "C" {
 
 size_t hippo_pattern_separation_workspace_bytes(int32_t nf, int32_t h, int32_t w, int32_t chunk_pairs) {
+  (void)chunk_pairs;
   if (nf < 0 || h <= 0 || w <= 0) return 256;
-  return hippo::pattern_layout(nullptr, 0, nf, h, w, chunk_pairs).bytes;
+  return hippo::pattern_layout(nullptr, 0, nf, h, w).bytes;
 }
 
 hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t h, int32_t w, int32_t ch,
@@ -118,9 +108,11 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
                                       int32_t* out_count, int32_t max_segments, void* ws, size_t ws_bytes,
                                       void* const* side_streams_host, void* stream) {
   using namespace hippo;
+  (void)chunk_pairs;                              // the first version took the frames in chunks; one SSIM launch now
   const bool has_video = frames != nullptr && frame_times != nullptr && nf > 0;
   const bool has_audio = pcm != nullptr;
   HIPPO_REQUIRE(nf >= 0 && (!has_video || (h >= 1 && w >= 1 && (ch == 1 || ch == 3))), "hippo_pattern_separation: bad frame shape");
+  HIPPO_REQUIRE(!has_video || (nf <= 65535 && w <= 65535 && h <= 65535), "hippo_pattern_separation: at most 65535 frames of 65535 x 65535");
   HIPPO_REQUIRE(!has_video || nf < 2 || (out_ssim && out_mse), "hippo_pattern_separation: out_ssim / out_mse missing");
   HIPPO_REQUIRE(!has_audio || (ns >= 0 && nch >= 1 && out_e16 && out_e512), "hippo_pattern_separation: bad audio arguments");
   HIPPO_REQUIRE(out_bounds && out_count && max_segments >= 1, "hippo_pattern_separation: bad output arguments");
@@ -128,51 +120,40 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   hippo_status st = check_arch();
   if (st != HIPPO_OK) return st;
   const int nfv = has_video ? nf : 0;
-  PatternLayout L = pattern_layout(ws, ws_bytes, nfv, h, w, chunk_pairs);
+  PatternLayout L = pattern_layout(ws, ws_bytes, nfv, h, w);
   if (ws == nullptr || ((uintptr_t)ws & 255) || L.bytes > ws_bytes) {
     set_error("hippo_pattern_separation: workspace of %zu bytes needed (256-byte aligned), got %zu", L.bytes, ws_bytes);
     return HIPPO_E_WORKSPACE;
   }
   cudaStream_t main = (cudaStream_t)stream;
-  cudaStream_t lane[2] = {(cudaStream_t)side_streams_host[0], (cudaStream_t)side_streams_host[1]};
+  cudaStream_t lane = (cudaStream_t)side_streams_host[0];
+  cudaStream_t aux = (cudaStream_t)side_streams_host[1];
   cudaStream_t chain = (cudaStream_t)side_streams_host[2];
-  const int cp = pattern_chunk(nfv, chunk_pairs);
-  // SSIM chunks: whole chunks of cp pairs (444 = one wave of SSIM CTAs); a small remainder stays its own last chunk:
-  // it runs beside the chunk before it (alternating streams), and the shorter the last chunk, the fewer segments are
-  // left for the final pass of the chain -- the only part of the chain nothing can hide
-  std::vector<int> cuts;                       // first pair of every chunk, then the number of pairs
-  if (nfv > 1) {
-    for (int f = 0; f < nfv - 1; f += cp) cuts.push_back(f);
-    cuts.push_back(nfv - 1);
-  }
-  const int nchunks = cuts.empty() ? 0 : (int)cuts.size() - 1;
+  const bool scored = nfv > 1;                                  // there are adjacent pairs to score
+  const bool follow = scored && pattern_follow();
   size_t ev = 0;
-  cudaEvent_t e_start = pooled_event(ev++);
-  HIPPO_REQUIRE(e_start != nullptr, "hippo_pattern_separation: could not create events");
+  cudaEvent_t e_start = pooled_event(ev++), e_init = pooled_event(ev++), e_pairs = pooled_event(ev++),
+              e_audio = pooled_event(ev++), e_done = pooled_event(ev++);
+  HIPPO_REQUIRE(e_start && e_init && e_pairs && e_audio && e_done, "hippo_pattern_separation: could not create events");
   HIPPO_CUDA(cudaEventRecord(e_start, main));
-  HIPPO_CUDA(cudaStreamWaitEvent(lane[0], e_start, 0));
   HIPPO_CUDA(cudaStreamWaitEvent(chain, e_start, 0));
 
-  // HIPPO_PATTERN_DEBUG: a timeline of the chunks and of the chain launches (timing events, synchronises at the end)
+  // HIPPO_PATTERN_DEBUG: a timeline of the launches (timing events, synchronises at the end)
   const bool dbg = getenv("HIPPO_PATTERN_DEBUG") != nullptr;
-  struct Mark { cudaEvent_t e; const char* what; int i; };
+  struct Mark { cudaEvent_t e; const char* what; };
   std::vector<Mark> marks;
-  auto mark = [&](cudaStream_t s, const char* what, int i) {
+  auto mark = [&](cudaStream_t s, const char* what) {
     if (!dbg) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
-    marks.push_back({e, what, i});
+    marks.push_back({e, what});
   };
-  mark(main, "start", 0);
+  mark(main, "start");
 
-  // chain stream: audio pyramid, stream descriptor + fresh state
-  if (has_audio) {
-    st = hippo_audio_energy(pcm, pcm_dtype, ns, nch, out_e16, out_e512, chain);
-    if (st != HIPPO_OK) return st;
-  }
+  // chain stream: stream descriptor + fresh state (+ pending marks), then the follower at once
   hippo_stream_desc d{};
-  d.ssim = nfv > 1 ? out_ssim : nullptr;
+  d.ssim = scored ? out_ssim : nullptr;
   d.frame_times = has_video ? frame_times : nullptr;
   d.nframes = nfv;
   d.pcm = pcm;
@@ -185,88 +166,58 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   d.out_bounds = out_bounds;
   d.out_count = out_count;
   d.max_segments = max_segments;
-  const bool follow = nchunks > 0 && pattern_follow(nfv);
-  pattern_init_kernel<<<follow ? 8 : 1, 256, 0, chain>>>(L.desc, L.state, d, L.counters, kPatternMaxChunks,
-                                                         follow ? L.pair_done : nullptr, out_ssim, nfv - 1);
+  unsigned int* audio_flag = L.pair_done + (scored ? nfv - 1 : 0);
+  pattern_init_kernel<<<scored ? 8 : 1, 256, 0, chain>>>(L.desc, L.state, d, scored ? L.pair_done : nullptr, out_ssim,
+                                                         nfv - 1);
   HIPPO_CUDA(cudaGetLastError());
-  cudaEvent_t e_init = pooled_event(ev++);
-  HIPPO_REQUIRE(e_init != nullptr, "hippo_pattern_separation: could not create events");
   HIPPO_CUDA(cudaEventRecord(e_init, chain));
-  const size_t chain_smem = 0;
   if (follow) {
-    // the chain, ONE launch that follows the SSIM kernels pair by pair from an SM of its own (segment.cu): 220 KB of
-    // dynamic shared memory leave no room for a gray (12 KB static) or SSIM (8 KB dynamic) CTA beside it.  A wait
-    // beyond the limit (HIPPO_FOLLOW_US, default 4 ms) suspends it; the final pass below picks up whatever is left.
+    // the chain, ONE launch that follows the SSIM warps pair by pair from an SM of its own (segment.cu).  It goes
+    // first: the GPU is idle, so it is resident before the frame kernels fill every SM, and 220 KB of dynamic shared
+    // memory leave no room beside it for their CTAs (12 KB static / 8 KB dynamic).  A wait beyond the limit
+    // (HIPPO_FOLLOW_US, default 4 ms) suspends it; the final pass below picks up whatever is left.
     const char* fe = getenv("HIPPO_FOLLOW_US");
     const long long follow_ns = 1000ll * (fe && atoll(fe) > 0 ? atoll(fe) : 4000);
-    mark(chain, "follow begin", 0);
     st = segment_resume_launch(L.desc, 1, L.state, 0, 0, max_segment_duration, min_segment_duration,
-                               frame_similarity_threshold, audio_silence_threshold, (size_t)220 * 1024, follow_ns, chain);
+                               frame_similarity_threshold, audio_silence_threshold, (size_t)220 * 1024, follow_ns,
+                               audio_flag, chain);
     if (st != HIPPO_OK) return st;
-    mark(chain, "follow end", 0);
+    mark(chain, "follow end");
   }
-  // persistent SSIM warps (dynamic item queue) finish the SSIM phase sooner (444 vs 483 us per stream-hour) but crowd
-  // the boundary chain, which then ends later: off unless HIPPO_SSIM_PERSISTENT=1
-  const bool persistent = getenv("HIPPO_SSIM_PERSISTENT") && atoi(getenv("HIPPO_SSIM_PERSISTENT")) == 1;
-  const char* fine_env = getenv("HIPPO_SSIM_FINE");
-  const int fine_bh = fine_env ? atoi(fine_env) : 56;
-
-  if (nchunks > 0) {
-    // lane 0: BGR -> gray (+ min / max) of ALL frames, once.  It is HBM bound; the SSIM kernels are issue bound, but
-    // letting them overlap does not pay: the conversion streams 0.7 GB through L2 and evicts the gray rows the SSIM
-    // warps are reading (measured: chunks of gray + SSIM on alternating streams were slower than no overlap at all)
-    st = frames_gray_launch(frames, nfv, h, w, ch, L.lane_ws[0], L.lane_bytes, lane[0]);
+  if (has_audio) {
+    // before the frame kernels in launch order: behind them it would wait for an SM until they drain
+    HIPPO_CUDA(cudaStreamWaitEvent(aux, e_init, 0));
+    st = hippo_audio_energy(pcm, pcm_dtype, ns, nch, out_e16, out_e512, aux);
     if (st != HIPPO_OK) return st;
-    cudaEvent_t e_gray = pooled_event(ev++);
-    HIPPO_REQUIRE(e_gray != nullptr, "hippo_pattern_separation: could not create events");
-    HIPPO_CUDA(cudaEventRecord(e_gray, lane[0]));
-    HIPPO_CUDA(cudaStreamWaitEvent(lane[1], e_gray, 0));
-    HIPPO_CUDA(cudaStreamWaitEvent(lane[0], e_init, 0));     // counters cleared
-    HIPPO_CUDA(cudaStreamWaitEvent(lane[1], e_init, 0));
-    mark(lane[0], "gray end", 0);
+    if (follow) pattern_flag_kernel<<<1, 1, 0, aux>>>(audio_flag);
+    mark(aux, "pyramid end");
+    HIPPO_CUDA(cudaEventRecord(e_audio, aux));
   }
-  for (int i = 0; i < nchunks; ++i) {
-    // SSIM of pairs [p0, p1) on alternating streams: the CTAs of chunk i + 1 fill the SMs as chunk i drains
-    const int p0 = cuts[i], p1 = cuts[i + 1];
-    cudaStream_t s = lane[i & 1];
-    // the chunks that end the stream use bands half as high: twice as many, shorter items, so the SMs run
-    // dry within ~25 us of each other instead of ~50 (everything before is followed by more work anyway)
-    const int bh = (nfv - 1 - p0 <= cp + cp / 2) ? fine_bh : 56;
-    st = frames_ssim_launch(nfv, h, w, L.lane_ws[0], L.lane_bytes, p0, p1, bh,
-                            (persistent && !follow) ? L.counters + i : nullptr, follow ? L.pair_done : nullptr, out_ssim,
-                            out_mse, s);
+  if (scored) {
+    // lane: gray + SSIM of every adjacent pair behind the pending marks, held back until the follower is resident
+    HIPPO_CUDA(cudaStreamWaitEvent(lane, e_init, 0));
+    if (follow) pattern_wait_kernel<<<1, 1, 0, lane>>>(audio_flag + 1, 100000);
+    st = frames_adjacent_live_launch(frames, nfv, h, w, ch, L.frame_ws, L.frame_bytes, L.pair_done, out_ssim, out_mse, lane);
     if (st != HIPPO_OK) return st;
-    mark(s, "chunk end", i);
-    const bool last = i == nchunks - 1;
-    if (follow && i < nchunks - 2) continue;       // streams are in order: the last event of either lane covers the lane
-    cudaEvent_t e = pooled_event(ev++);
-    HIPPO_REQUIRE(e != nullptr, "hippo_pattern_separation: could not create events");
-    HIPPO_CUDA(cudaEventRecord(e, s));
-    HIPPO_CUDA(cudaStreamWaitEvent(chain, e, 0));
-    if (follow && !last) continue;                 // one final pass behind everything (a no-op when the chain got through)
-    mark(chain, "chain begin", i);
-    // pairs < p1 are final, i.e. frames < p1 + 1 are covered (every earlier chunk's event was waited for above)
-    st = segment_resume_launch(L.desc, 1, L.state, p1 + 1, last ? 1 : 0, max_segment_duration, min_segment_duration,
-                               frame_similarity_threshold, audio_silence_threshold, chain_smem, 0, chain);
-    if (st != HIPPO_OK) return st;
-    mark(chain, "chain end", i);
+    mark(lane, "pairs end");
+    HIPPO_CUDA(cudaEventRecord(e_pairs, lane));
   }
-  if (nchunks == 0) {
-    st = segment_resume_launch(L.desc, 1, L.state, nfv, 1, max_segment_duration, min_segment_duration,
-                               frame_similarity_threshold, audio_silence_threshold, 0, 0, chain);
-    if (st != HIPPO_OK) return st;
-  }
-  cudaEvent_t e_done = pooled_event(ev++);
-  HIPPO_REQUIRE(e_done != nullptr, "hippo_pattern_separation: could not create events");
+  // final pass behind everything: a no-op when the follower got through
+  if (scored) HIPPO_CUDA(cudaStreamWaitEvent(chain, e_pairs, 0));
+  if (has_audio) HIPPO_CUDA(cudaStreamWaitEvent(chain, e_audio, 0));
+  st = segment_resume_launch(L.desc, 1, L.state, nfv, 1, max_segment_duration, min_segment_duration,
+                             frame_similarity_threshold, audio_silence_threshold, 0, 0, nullptr, chain);
+  if (st != HIPPO_OK) return st;
+  mark(chain, "final pass end");
   HIPPO_CUDA(cudaEventRecord(e_done, chain));
   HIPPO_CUDA(cudaStreamWaitEvent(main, e_done, 0));
   if (dbg) {
-    mark(main, "joined", 0);
+    mark(main, "joined");
     cudaStreamSynchronize(main);
     for (size_t i = 1; i < marks.size(); ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, marks[0].e, marks[i].e);
-      fprintf(stderr, "[pattern] %8.1f us  %s %d\n", ms * 1e3f, marks[i].what, marks[i].i);
+      fprintf(stderr, "[pattern] %8.1f us  %s\n", ms * 1e3f, marks[i].what);
     }
     for (auto& m : marks) cudaEventDestroy(m.e);
   }

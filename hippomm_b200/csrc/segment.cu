@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
                                                                  double ssim_thr, double db_thr,
                                                                  hippo_segment_state* __restrict__ states,
                                                                  int64_t frames_ready, int final_pass,
-                                                                 long long follow_ns, unsigned long long* dbg) {
+                                                                 long long follow_ns,
+                                                                 const unsigned int* __restrict__ follow_gate,
+                                                                 unsigned long long* dbg) {
   extern __shared__ double s_stage[];          // [kStageFrames] frame times, [kStageFrames] ssim
   // per-segment results, triple-buffered so that ONE barrier per segment suffices: segment k uses set k % 3,
   // the last thread re-arms set (k + 1) % 3 at the start of segment k (last read in segment k - 2, which every thread
@@ -176,13 +178,16 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   if (si >= nstreams) return;
   const hippo_stream_desc S = streams[si];
 
+  // follow mode: tell the host-side launch order that this CTA is resident (pattern.cu holds the frame kernels back
+  // until then: once they fill every SM, no SM would ever drain for a CTA that wants one to itself)
+  if (follow_ns > 0 && follow_gate != nullptr && tid == 0) st_volatile_u32(const_cast<unsigned int*>(follow_gate) + 1, 1u);
   if (states != nullptr && states[si].done) return;
   const bool has_video = S.frame_times != nullptr && S.nframes > 0;   // `if video_frames and frame_times`
   const bool has_audio = S.pcm != nullptr && S.sample_rate != 0.0;    // `audio_data is not None and audio_sample_rate`
   const double sr = S.sample_rate;
   const int64_t nf = S.nframes;
-  // follow mode needs the staged copy (the host only asks for it when the frames fit)
-  const bool follow = follow_ns > 0 && states != nullptr && has_video && nf <= kStageFrames;
+  const bool follow = follow_ns > 0 && states != nullptr && has_video;
+  const bool staged = has_video && nf <= kStageFrames;    // longer streams: times and SSIMs straight from global memory
 
   const double* ftimes = S.frame_times;
   const double* ssim = S.ssim;
@@ -220,6 +225,25 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
   else {
     if (tid == 0) { *S.out_count = 0; if (states != nullptr) states[si].done = 1; }
     return;
+  }
+
+  if (follow) {
+    // The follower is launched FIRST (an idle GPU gives it its SM at once); nothing it reads is final yet.  Gate: the
+    // audio pyramid (a flag stored by a launch behind it) and the first pair's SSIM.
+    if (tid == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      for (;;) {
+        const bool audio_ok = follow_gate == nullptr || !has_audio || ld_volatile_u32(follow_gate) != 0;
+        const bool video_ok = S.ssim == nullptr || nf < 2 ||
+                              __double_as_longlong(ld_volatile_f64(S.ssim)) != (long long)kSsimPending;
+        if (audio_ok && video_ok) break;
+        if (globaltimer_ns() - t0 > (unsigned long long)follow_ns) { s_abort = 1; break; }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+    if (s_abort) return;                       // state untouched: the final pass starts from it
+    __threadfence();
   }
 
   const double pow_thr = pow(10.0, db_thr / 10.0);
@@ -266,13 +290,13 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
             const double tp = i > hint ? ftimes[i - 1] : -INFINITY;
             if (t >= cs && !(tp >= cs)) s_lo[set] = i;                       // the unique first frame of the run
             if (ssim != nullptr && i > hint && tp >= cs && t <= ce) {
-              double sv = ssim[i - 1];
+              double sv = (follow && !staged) ? ld_volatile_f64(S.ssim + (i - 1)) : ssim[i - 1];
               if (follow && __double_as_longlong(sv) == (long long)kSsimPending) {
                 // the pair's SSIM warp has not delivered yet: poll its result, keep it for the later segments
                 const unsigned long long t0 = globaltimer_ns();
                 for (;;) {
                   sv = ld_volatile_f64(S.ssim + (i - 1));
-                  if (__double_as_longlong(sv) != (long long)kSsimPending) { s_stage[kStageFrames + i - 1] = sv; break; }
+                  if (__double_as_longlong(sv) != (long long)kSsimPending) { if (staged) s_stage[kStageFrames + i - 1] = sv; break; }
                   if (globaltimer_ns() - t0 > (unsigned long long)follow_ns) { s_abort = 1; break; }
                   __nanosleep(40);
                 }
@@ -372,7 +396,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
 static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nstreams, double max_segment_duration,
                                    double min_segment_duration, double frame_similarity_threshold,
                                    double audio_silence_threshold, hippo_segment_state* states, int64_t frames_ready,
-                                   int final_pass, void* stream, size_t smem_reserve = 0, long long follow_ns = 0) {
+                                   int final_pass, void* stream, size_t smem_reserve = 0, long long follow_ns = 0,
+                                   const unsigned int* follow_gate = nullptr) {
   using namespace hippo;
   HIPPO_REQUIRE(nstreams >= 0, "hippo_segment_boundaries: nstreams < 0");
   if (nstreams == 0) return HIPPO_OK;
@@ -387,7 +412,7 @@ static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nst
   if (getenv("HIPPO_SEG_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
   segment_kernel<<<nstreams, kSegThreads, smem, (cudaStream_t)stream>>>(
       streams, nstreams, max_segment_duration, min_segment_duration, frame_similarity_threshold,
-      audio_silence_threshold, states, frames_ready, final_pass, follow_ns, dbg);
+      audio_silence_threshold, states, frames_ready, final_pass, follow_ns, follow_gate, dbg);
   if (dbg) {
     unsigned long long h[8];
     cudaStreamSynchronize((cudaStream_t)stream);
@@ -403,9 +428,10 @@ static hippo_status launch_segment(const hippo_stream_desc* streams, int32_t nst
 namespace hippo {
 hippo_status segment_resume_launch(const hippo_stream_desc* streams, int32_t nstreams, hippo_segment_state* states,
                                    int64_t frames_ready, int final_pass, double max_dur, double min_dur, double ssim_thr,
-                                   double db_thr, size_t smem_reserve, long long follow_ns, cudaStream_t s) {
+                                   double db_thr, size_t smem_reserve, long long follow_ns,
+                                   const unsigned int* follow_gate, cudaStream_t s) {
   return launch_segment(streams, nstreams, max_dur, min_dur, ssim_thr, db_thr, states, frames_ready, final_pass, (void*)s,
-                        smem_reserve, follow_ns);
+                        smem_reserve, follow_ns, follow_gate);
 }
 int segment_stage_frames() { return kStageFrames; }
 }  // namespace hippo

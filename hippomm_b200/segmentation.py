@@ -314,14 +314,14 @@ def pattern_separation_device(frames: Optional[torch.Tensor], frame_times: Optio
     """Temporal pattern separation of ONE stream resident on the device, its stages overlapped
     (`hippo_pattern_separation`: ONE C-ABI call issues every launch).
 
-    The frames are taken in chunks of `chunk_pairs` adjacent pairs (444 = three SSIM CTAs per SM on 148 SMs: one
-    wave).  Chunks alternate between two side streams, so the HBM-bound gray conversion of chunk i + 1 runs under
-    the issue-bound SSIM kernel of chunk i; the audio pyramid runs on a third stream, and so does the boundary
-    state machine in its resumable form: after every second chunk it takes the segments whose 30 s window is
-    already covered by finished SSIM values and suspends, so only the last few segments' chain is left when the
-    last chunk is done.  No kernel waits for another kernel (stream events only).  Results are identical to the
-    three stage-by-stage calls.  `slot` picks one of several independent sets of side streams / scratch, so that
-    calls for different streams issued from different CUDA streams can overlap each other.
+    The boundary state machine is launched first, in follow mode: one CTA on an SM of its own that polls each pair's
+    SSIM as the SSIM warps deliver it, so the sequential chain ends a few microseconds after the last pair instead of
+    0.23 ms later.  The audio pyramid runs on a second side stream, gray conversion + one SSIM launch on a third; a
+    final resumable pass behind everything completes the chain if the follower gave up waiting (serialising
+    profilers, launch-blocking debug runs).  Results are identical to the three stage-by-stage calls.
+    `chunk_pairs` is ignored (the first version took the frames in chunks).  `slot` picks one of several independent
+    sets of side streams / scratch, so that calls for different streams issued from different CUDA streams can
+    overlap each other.
     Returns (bounds fp64 [max_segments, 2], count int32 [1], ssim fp64 [nf - 1] or None)."""
     lib = _lib.load()
     ref = frames if frames is not None else pcm
