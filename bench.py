@@ -1075,8 +1075,9 @@ def run_extras(bank, q_dev, peaks, device, lib):
                          "frac": bytes_ / t_all / 1e9 / peaks["hbm"], "algorithmic_bytes": bytes_,
                          "note": "whole pass (gray + SSIM + audio pyramid + boundary chain); the SSIM kernel is "
                                  "integer-issue bound, not HBM bound (DESIGN.md 4.4)"},
-            "config": "3600 frames 224x224x3 uint8 + 57.6M int16 samples, resident in HBM; one stream; chunks of 444 "
-                      "frame pairs on two alternating CUDA streams, audio pyramid and the resumable boundary chain on a third",
+            "config": "3600 frames 224x224x3 uint8 + 57.6M int16 samples, resident in HBM; one stream; the boundary "
+                      "chain follows the SSIM warps pair by pair from an SM of its own (one launch, launched first), "
+                      "audio pyramid on a second stream, gray conversion + one SSIM launch on a third",
         }
         log(f"[extra] segmentation {t_all * 1e3:.3f} ms per stream-hour overlapped ({t_serial * 1e3:.3f} ms stage by stage, "
             f"{t_stream * 1e3:.3f} ms streaming kernels alone)")

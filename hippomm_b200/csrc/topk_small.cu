@@ -1,4 +1,4 @@
-// topk_small: 3 .. 64 queries against the bank in ONE pass at (close to) HBM speed.
+// topk_small: 3 .. 128 queries against the bank in ONE pass at (close to) HBM speed.
 //
 // Reference: a handful of sequential top_k_cosine_similarity calls (vo:151-188) -- each of them a full pass over the
 // bank.  Between the single-query GEMV (topk_single.cu, HBM bound) and the 256-query tiles of sim_tc.cu (tensor
@@ -6,9 +6,10 @@
 // sim_tc.cu such a batch costs 4.3 - 4.8 ms over 10M rows (3.1 ms is the HBM floor): its 256-row query tile is mostly
 // padding and is re-fetched for every bank tile, so half of every pipeline stage -- half of the bytes in flight -- is
 // not bank at all.  Here the operands swap roles:
-//   * M = 128 BANK rows per tile (TMEM lanes), N = 32 or 64 QUERIES (TMEM columns), tcgen05.mma cta_group::1;
+//   * M = 128 BANK rows per tile (TMEM lanes), N = 32, 64 or 128 QUERIES (TMEM columns), tcgen05.mma cta_group::1;
 //   * a stage holds 16 KB of bank and only 4 / 8 KB of queries, so 11 / 9 stages fit: 176 / 144 KB of bank in
-//     flight per SM instead of 96;
+//     flight per SM instead of 96 (128 queries: 16 KB, 6 stages, 96 KB -- as many as through sim_tc.cu, but every
+//     tensor-core cycle works on real queries instead of a tile that is half padding);
 //   * one CTA per SM, no clusters: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (one TMEM lane quarter
 //     each); two accumulators, so the MMAs of tile t + 1 run under the epilogue of tile t.
 // Epilogue: a thread owns one bank row and looks at its N dots: dot / |b| against the per-query threshold (k-th best
@@ -181,63 +182,71 @@ topk_small_kernel(const __grid_constant__ CUtensorMap tmBank, const __grid_const
       }
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
-      uint32_t v[NP];
-#pragma unroll
-      for (int c = 0; c < NP / 32; ++c) {
-        uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32 * c]);
-        tmem_ld_32x32(lane_addr + buf * NP + c * 32, chunk);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);          // the accumulator is in registers: the next MMAs may start
-
       const bool in = row < p.n;
       const float inv = __frcp_rn(bn);                     // zero / non-finite norm: NaN or inf below, passes the filter
-      uint64_t hits = 0;
+      // the thread's NP dots in groups of up to 64 columns (registers); the accumulator is handed back to the MMA
+      // warp as soon as the last group is in registers
+      constexpr int G = NP < 64 ? NP : 64;
 #pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const float tv = __uint_as_float(v[j]) * inv;
-        hits |= (!(tv < s_thr[j])) ? (1ull << j) : 0ull;   // NaN passes (vo:185 ranks NaN first)
-      }
-      if (!in) hits = 0;
-      while (hits) {
-        const int j = __ffsll((long long)hits) - 1;
-        hits &= hits - 1;
-        if (j >= p.nq) continue;
-        // v[j] for a run-time j without local memory: select tree over the registers
-        uint32_t raw;
-        if constexpr (NP == 32) {
-          raw = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), j);
-        } else {
-          const uint32_t lo = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), j & 31);
-          const uint32_t hi = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[32]), j & 31);
-          raw = (j & 32) ? hi : lo;
+      for (int g = 0; g < NP / G; ++g) {
+        uint32_t v[G];
+#pragma unroll
+        for (int c = 0; c < G / 32; ++c) {
+          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32 * c]);
+          tmem_ld_32x32(lane_addr + buf * NP + g * G + c * 32, chunk);
         }
-        const float dot = __uint_as_float(raw);
-        const float an = s_an[j];
-        if (dot * inv < s_thr[j]) continue;                // the threshold moved meanwhile
-        // the reference's operation order (vo:182): dot / (|b| * |a|), IEEE fp32
-        const float sc = __fdiv_rn(dot, __fmul_rn(bn, an));
-        const uint64_t key = pack_key(sc, (uint32_t)(p.row_base + row));
-        if (!(key < s_below[j])) continue;
-        uint64_t* L = lists + j * HIPPO_TOPK_MAX;
-        bool done = false;
-        while (!done) {
-          if (atomicCAS(&s_lock[j], 0u, 1u) == 0u) {
-            __threadfence_block();
-            if (key > L[k - 1]) {
-              int i = k - 1;
-              while (i > 0 && L[i - 1] < key) { L[i] = L[i - 1]; --i; }
-              L[i] = key;
-              if (an > 0.f && an < INFINITY) {
-                const float cand = small_threshold(L[k - 1], 0u, an);
-                if (cand > s_thr[j]) s_thr[j] = cand;
+        tmem_ld_wait();
+        if (g == NP / G - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);        // the accumulator is in registers: the next MMAs may start
+        }
+        uint64_t hits = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float tv = __uint_as_float(v[j]) * inv;
+          hits |= (!(tv < s_thr[g * G + j])) ? (1ull << j) : 0ull;   // NaN passes (vo:185 ranks NaN first)
+        }
+        if (!in) hits = 0;
+        while (hits) {
+          const int jl = __ffsll((long long)hits) - 1;
+          hits &= hits - 1;
+          const int j = g * G + jl;
+          if (j >= p.nq) continue;
+          // v[jl] for a run-time jl without local memory: select tree over the registers
+          uint32_t raw;
+          if constexpr (G == 32) {
+            raw = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), jl);
+          } else {
+            const uint32_t lo = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), jl & 31);
+            const uint32_t hi = select32(*reinterpret_cast<const uint32_t(*)[32]>(&v[32]), jl & 31);
+            raw = (jl & 32) ? hi : lo;
+          }
+          const float dot = __uint_as_float(raw);
+          const float an = s_an[j];
+          if (dot * inv < s_thr[j]) continue;                // the threshold moved meanwhile
+          // the reference's operation order (vo:182): dot / (|b| * |a|), IEEE fp32
+          const float sc = __fdiv_rn(dot, __fmul_rn(bn, an));
+          const uint64_t key = pack_key(sc, (uint32_t)(p.row_base + row));
+          if (!(key < s_below[j])) continue;
+          uint64_t* L = lists + j * HIPPO_TOPK_MAX;
+          bool done = false;
+          while (!done) {
+            if (atomicCAS(&s_lock[j], 0u, 1u) == 0u) {
+              __threadfence_block();
+              if (key > L[k - 1]) {
+                int i = k - 1;
+                while (i > 0 && L[i - 1] < key) { L[i] = L[i - 1]; --i; }
+                L[i] = key;
+                if (an > 0.f && an < INFINITY) {
+                  const float cand = small_threshold(L[k - 1], 0u, an);
+                  if (cand > s_thr[j]) s_thr[j] = cand;
+                }
               }
+              __threadfence_block();
+              atomicExch(&s_lock[j], 0u);
+              done = true;
             }
-            __threadfence_block();
-            atomicExch(&s_lock[j], 0u);
-            done = true;
           }
         }
       }
@@ -288,12 +297,13 @@ static hippo_status small_tmap(CUtensorMap* tm, const void* base, int64_t rows, 
   return HIPPO_OK;
 }
 
-// 3 .. 64 queries of a dimension that is a multiple of 64.  HIPPO_SMALL_BATCH=0 sends them through sim_tc.cu instead.
+// 3 .. 128 queries of a dimension that is a multiple of 64.  HIPPO_SMALL_BATCH=0 sends them through sim_tc.cu instead
+// (HIPPO_SMALL_BATCH=64: only up to 64 queries, the A/B switch for the 128-query tile).
 bool topk_small_supported(int d, int nq) {
-  static const bool off = getenv("HIPPO_SMALL_BATCH") && atoi(getenv("HIPPO_SMALL_BATCH")) == 0;
-  return !off && d % 64 == 0 && nq >= 3 && nq <= 64;
+  static const int lim = getenv("HIPPO_SMALL_BATCH") ? atoi(getenv("HIPPO_SMALL_BATCH")) : 128;
+  return lim > 0 && d % 64 == 0 && nq >= 3 && nq <= (lim < 128 ? lim : 128);
 }
-int topk_small_npad(int nq) { return nq <= 32 ? 32 : 64; }
+int topk_small_npad(int nq) { return nq <= 32 ? 32 : (nq <= 64 ? 64 : 128); }
 int topk_small_grid(int64_t n) {
   const int64_t tiles = (n + kSmBM - 1) / kSmBM;
   const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -325,9 +335,12 @@ hippo_status topk_small_launch(const void* bank, const float* norm, int64_t n, i
   if (npad == 32) {
     HIPPO_CUDA(cudaFuncSetAttribute(topk_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmallCfg<32>::kSmem));
     topk_small_kernel<32><<<grid, kSmThreads, SmallCfg<32>::kSmem, s>>>(tmBank, tmQ, p);
-  } else {
+  } else if (npad == 64) {
     HIPPO_CUDA(cudaFuncSetAttribute(topk_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmallCfg<64>::kSmem));
     topk_small_kernel<64><<<grid, kSmThreads, SmallCfg<64>::kSmem, s>>>(tmBank, tmQ, p);
+  } else {
+    HIPPO_CUDA(cudaFuncSetAttribute(topk_small_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmallCfg<128>::kSmem));
+    topk_small_kernel<128><<<grid, kSmThreads, SmallCfg<128>::kSmem, s>>>(tmBank, tmQ, p);
   }
   HIPPO_CUDA(cudaGetLastError());
   *nparts_out = grid;

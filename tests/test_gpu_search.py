@@ -112,10 +112,10 @@ def test_ragged_shapes_both_paths_agree_with_oracle(cuda_device, n, d, nq, k):
             assert np.all(idx[qi][kk:] == -1)
 
 
-@pytest.mark.parametrize("nq", [2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 64, 65])
+@pytest.mark.parametrize("nq", [2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 64, 65, 100, 128, 129])
 def test_few_queries_ride_one_bank_pass(cuda_device, nq):
     """A few queries of dimension 1024 behind the batched entry (two take the GEMV with two accumulators per row,
-    topk_single.cu; 3 .. 64 the small-batch tcgen05 kernel with the bank rows on the M side, topk_small.cu; more the
+    topk_single.cu; 3 .. 128 the small-batch tcgen05 kernel with the bank rows on the M side, topk_small.cu; more the
     256-query tiles of sim_tc.cu): bit-equal to the single-query kernel on the lattice bank, within the parity rule
     on Gaussian rows, NaN rows first, paging beyond HIPPO_TOPK_MAX, row counts off the 4-row groups / 128-row tiles."""
     from hippomm_b200 import MemoryBank, synth
