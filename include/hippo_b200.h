@@ -388,12 +388,15 @@ hippo_status hippo_segment_boundaries_resume(const hippo_stream_desc* streams, i
                                              double audio_silence_threshold, void* stream);
 
 /*
- * One stream, all stages, overlapped (hm:1002-1114 with hm:980-1000 underneath): the frames are taken in
- * chunks of `chunk_pairs` adjacent pairs (0 = 444) whose gray conversion + SSIM alternate between
- * side_streams_host[0] and [1]; the audio pyramid and the resumable boundary state machine run on
- * side_streams_host[2], the chain advancing after every second chunk.  `stream` is joined at both ends
- * (events), so the call behaves like any other asynchronous call on `stream`.  The results equal
+ * One stream, all stages, overlapped (hm:1002-1114 with hm:980-1000 underneath).  The boundary state machine is
+ * launched FIRST on side_streams_host[2] (give it a high-priority stream) in follow mode: one CTA on an SM of its
+ * own that polls each adjacent pair's SSIM as the SSIM warps deliver it; the audio pyramid runs on
+ * side_streams_host[1], gray conversion + one SSIM launch on side_streams_host[0]; a final resumable pass on [2]
+ * behind everything completes the chain if the follower gave up waiting (it never waits longer than 4 ms, env
+ * HIPPO_FOLLOW_US: serialising profilers and launch-blocking debug runs stay correct).  `stream` is joined at both
+ * ends (events), so the call behaves like any other asynchronous call on `stream`.  The results equal
  * hippo_frame_pairs + hippo_audio_energy + hippo_segment_boundaries run one after the other.
+ * `chunk_pairs` is ignored (kept for ABI v2: the first version took the frames in chunks).
  *   frames / frame_times  NULL = no video;  pcm NULL = no audio (then out_e16 / out_e512 may be NULL)
  *   out_ssim, out_mse     [nf - 1] fp64;  out_e16 [ceil(ns/16)], out_e512 [ceil(ns/512)] fp64
  *   side_streams_host     HOST array of three cudaStream_t distinct from `stream` and from each other

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from hippomm_b200 import MemoryBank, synth, _cuda
 import bench
-n = int(os.environ.get("ROWS", 10_000_000)); d = 1024; nq = 4096
+n = int(os.environ.get("ROWS", 10_000_000)); d = 1024; nq = int(os.environ.get("NQ", 4096))
 dev = torch.device("cuda", 0)
 bank = MemoryBank(n, d, device=dev)
 bench.build_bank(bank, n, 0, n, dev)
