@@ -769,9 +769,12 @@ hippo_status tc_topk_launch(const TcTopkArgs& a, cudaStream_t s) {
   p.after_key = a.after_key;
   p.part = a.part;
   p.thr_ord = a.thr_ord;
-  // up to 256 queries every pair scans its own part of the bank for the SAME few queries: the shared pool would be a
-  // handful of cache lines hammered by every SM (7.0 ms for 8 queries against 3.9 ms for 64); the local lists suffice
-  p.pool = p.m_pairs >= 2 ? a.pool : nullptr;
+  // a handful of queries: every pair scans its own part of the bank for the SAME few queries and the shared pool is a
+  // handful of cache lines hammered by every SM (7.0 ms for 8 queries against 3.9 ms for 64) -- those batches take
+  // topk_small.cu now; from 129 queries on the pool pays (same box: 129 queries 4.31 -> 3.87 ms, 192: 5.18 -> 4.84,
+  // 256: 4.80 -> 4.63; HIPPO_TC_POOL_BLOCKS=2 restores the old rule)
+  static const int pool_blocks = getenv("HIPPO_TC_POOL_BLOCKS") ? atoi(getenv("HIPPO_TC_POOL_BLOCKS")) : 1;
+  p.pool = (p.m_pairs >= pool_blocks && (p.m_pairs >= 2 || a.nq > 128)) ? a.pool : nullptr;
   p.counters = a.counters;
   p.prog = a.progress;
   p.fc_window = flow_window();
