@@ -153,9 +153,6 @@ __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
 __device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
 __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
@@ -182,6 +179,13 @@ struct SsimArgs {
 
 // One (pair, band, chunk) item, by one warp; `item` numbers the items of ALL pairs (pair-major), `slot` is where its
 // partial sums go.
+//
+// Instruction budget of a row step (the kernel is issue / latency bound): the four row words come through
+// four running pointers (no per-row index arithmetic, no bounds test: lanes beyond the row read the row's first word, the
+// last step reads one row past the band -- the workspace carries a spare row -- and nothing such a value feeds is owned);
+// per column ONE byte permute yields (x, y, y, x) and a second its zero-extended halves x | y << 16, so that
+// x^2 + y^2 and 2 x y are one dp2a each and sum x | sum y << 16 advances by the difference of two permutes; the squared
+// error is accumulated by every lane and dropped at the end by the lanes that do not own their word.
 __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64_t slot, int lane) {
   const uint8_t* __restrict__ gray = A.gray;
   const int h = A.h, w = A.w, pitch = A.pitch, bh = A.bh, nbands = A.nbands, nchunks = A.nchunks;
@@ -197,8 +201,9 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   const int64_t gpix = A.gstride;
   const int wordx = (chunk * 30 + lane) * 4;                 // byte offset of this lane's word in a row
   const bool col_ok = wordx < pitch;
-  const uint8_t* ga = gray + (int64_t)fa * gpix + wordx;
-  const uint8_t* gb = gray + (int64_t)fb * gpix + wordx;
+  const int wordx_ld = col_ok ? wordx : 0;                   // what a lane beyond the row reads instead (never owned)
+  const uint8_t* ga = gray + (int64_t)fa * gpix + wordx_ld;
+  const uint8_t* gb = gray + (int64_t)fb * gpix + wordx_ld;
 
   // data range: hm:990 takes max - min of the FIRST frame in uint8; bp:61 fixes it at 1.0 on
   // the /255 scale, i.e. 255 on the integer scale
@@ -213,7 +218,6 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   const int y1 = min(y0 + bh, out_rows);          // window-top rows [y0, y1)
   const int rows_in = (y1 > y0) ? (y1 - y0 + 6) : 0;
   const int sse_r1 = (band == nbands - 1) ? h : min(y0 + bh, h);
-  const int rend = max(y0 + rows_in, sse_r1);
   // every image word is counted for the squared error by exactly one warp: chunks overlap by two words
   const bool sse_own = col_ok && (lane < 30 || chunk == nchunks - 1);
   // which of this lane's four windows exist and belong to this chunk
@@ -221,73 +225,88 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
 #pragma unroll
   for (int k = 0; k < 4; ++k) own[k] = lane < 30 && chunk * kSsimChunk + lane * 4 + k < out_cols;
 
-  // sliding 7-row column sums: sum x | sum y << 16, sum (x^2 + y^2) (the two variances only ever appear added), sum x y
-  int sp[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
+  // sliding 7-row column sums: sum x | sum y << 16, sum (x^2 + y^2) (the two variances only ever appear added), 2 sum x y
+  uint32_t sp[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
   double acc = 0.0;
   unsigned long long sse = 0;
   uint32_t sqe = 0, cr = 0;                       // sum a^2 + b^2, sum a b of the rows owned for the squared error
-  const uint64_t c1s2 = pack_f32x2(c1s, c1s), c2s2 = pack_f32x2(c2s, c2s), two2 = pack_f32x2(2.f, 2.f);
+  const uint64_t c1s2 = pack_f32x2(c1s, c1s), c2s2 = pack_f32x2(c2s, c2s);
 
   // One row step.  kFull: the row completes a 7-row window (horizontal sums + ratio) and the row that leaves the
   // window is fetched for the next step; kSse: this warp owns the row for the squared error.  The phases below
-  // call it with compile-time flags, so the steady state carries no per-row predicates: the only data-dependent
-  // address is the next row, clamped to the frame (its value is dead in the last step of a frame's last band).
+  // call it with compile-time flags, so the steady state carries no per-row predicates.
   static_assert(kSsimBand + 6 <= 4096, "sqe / cr hold rows x 4 bytes x 2 x 255^2 < 2^32 without a flush: at most 8,256 rows");
-  auto ldrow = [&](const uint8_t* g, int r) -> uint32_t {
-    return col_ok ? __ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * pitch)) : 0u;
-  };
+  const int pitch4 = pitch >> 2;                             // words per row (the pitch is a multiple of 4)
+  const uint32_t* ga4 = reinterpret_cast<const uint32_t*>(ga);
+  const uint32_t* gb4 = reinterpret_cast<const uint32_t*>(gb);
+  const uint32_t* pna = ga4 + (int64_t)(y0 + 1) * pitch4;    // the next row of either frame
+  const uint32_t* pnb = gb4 + (int64_t)(y0 + 1) * pitch4;
+  const uint32_t* poa = ga4 + (int64_t)y0 * pitch4;          // the next row to leave the window
+  const uint32_t* pob = gb4 + (int64_t)y0 * pitch4;
+  // four independent running pointers, one 64-bit multiply-add each per row (left to itself the compiler folds them
+  // into two running offsets and re-adds the bases for every load)
+  asm("" : "+l"(pna)); asm("" : "+l"(pnb)); asm("" : "+l"(poa)); asm("" : "+l"(pob));
   uint32_t wa = 0, wb = 0, oa = 0, ob = 0;
-  auto row_step = [&](int r, auto full_tag, auto sse_tag) {
+  auto row_step = [&](auto full_tag, auto sse_tag) {
     constexpr bool kFull = decltype(full_tag)::value, kSse = decltype(sse_tag)::value;
     // next row's words (and the row leaving the window): issued now, used in the next step
-    const int rn = min(r + 1, h - 1);
-    const uint32_t nwa = ldrow(ga, rn), nwb = ldrow(gb, rn);
+    const uint32_t nwa = __ldg(pna), nwb = __ldg(pnb);
+    pna += pitch4; pnb += pitch4;
     uint32_t noa = 0, nob = 0;
-    if constexpr (kFull) { noa = ldrow(ga, r - 6); nob = ldrow(gb, r - 6); }
-    if constexpr (kSse) {
-      if (sse_own) { sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr); }
+    if constexpr (kFull) {
+      noa = __ldg(poa); nob = __ldg(pob);
+      poa += pitch4; pob += pitch4;
     }
+    if constexpr (kSse) { sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr); }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int an = (int)byte_of(wa, k), bn = (int)byte_of(wb, k);
-      const int ao = (int)byte_of(oa, k), bo = (int)byte_of(ob, k);
-      const int da = an - ao, db = bn - bo;
-      sp[k] += da + db * 65536;                 // sum x | sum y << 16: the running sums never go negative
-      sq[k] += da * (an + ao) + db * (bn + bo);
-      sxy[k] += an * bn - ao * bo;
+      const uint32_t sel = (uint32_t)(k | ((4 + k) << 4) | ((4 + k) << 8) | (k << 12));
+      const uint32_t bn = __byte_perm(wa, wb, sel), hn = __byte_perm(bn, 0u, 0x4140);   // bytes (x, y, y, x); halves x | y << 16
+      sq[k] = __dp2a_lo(hn, bn, sq[k]);            // + x^2 + y^2
+      sxy[k] = __dp2a_hi(hn, bn, sxy[k]);          // + 2 x y
+      if constexpr (kFull) {
+        const uint32_t bo = __byte_perm(oa, ob, sel), ho = __byte_perm(bo, 0u, 0x4140);
+        sq[k] -= __dp2a_lo(ho, bo, 0u);
+        sxy[k] -= __dp2a_hi(ho, bo, 0u);
+        sp[k] += hn - ho;                          // the running sums never go negative
+      } else {
+        sp[k] += hn;
+      }
     }
     if constexpr (kFull) {
       // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
       // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
       int o_sp[4], o_sq[4], o_xy[4];
-      auto horiz = [&](const int (&c)[4], int (&o)[4]) {
+      auto horiz = [&](const uint32_t (&c)[4], int (&o)[4]) {
         // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
-        const int C = c[0] + c[1] + c[2], D = C + c[3];
-        const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c[3], 1);
-        const int m0 = __shfl_down_sync(0xffffffffu, c[0], 2), m1 = __shfl_down_sync(0xffffffffu, c[1], 2);
+        const int c0 = (int)c[0], c1 = (int)c[1], c2 = (int)c[2], c3 = (int)c[3];
+        const int C = c0 + c1 + c2, D = C + c3;
+        const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c3, 1);
+        const int m0 = __shfl_down_sync(0xffffffffu, c0, 2), m1 = __shfl_down_sync(0xffffffffu, c1, 2);
         o[0] = D + C1n;
-        o[1] = o[0] + n3 - c[0];
-        o[2] = o[1] + m0 - c[1];
-        o[3] = o[2] + m1 - c[2];
+        o[1] = o[0] + n3 - c0;
+        o[2] = o[1] + m0 - c1;
+        o[3] = o[2] + m1 - c2;
       };
       horiz(sp, o_sp); horiz(sq, o_sq); horiz(sxy, o_xy);
       float fu[4], fvs[4], fpxy[4], fvxy[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
-        const int pxy = sx * sy;
+        const int pxy2 = sx * (sy + sy);                    // 2 * 49^2 mu_x mu_y
         const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
         fu[k] = (float)u;
         fvs[k] = (float)(49 * o_sq[k] - u);                 // 48*49 (var_x + var_y), exact
-        fpxy[k] = (float)pxy;
-        fvxy[k] = (float)(49 * o_xy[k] - pxy);              // 48*49 cov_xy, exact
+        fpxy[k] = (float)pxy2;
+        fvxy[k] = (float)(49 * o_xy[k] - pxy2);             // 2 * 48*49 cov_xy, exact
       }
-      // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms)
+      // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms; the doubled
+      // integers convert to exactly twice the fp32 values, so `x2 + c` rounds like fma(2, x, c))
       float s4 = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; k += 2) {
-        const uint64_t a1 = fma_f32x2(two2, pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
-        const uint64_t a2 = fma_f32x2(two2, pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
+        const uint64_t a1 = add_f32x2(pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
+        const uint64_t a2 = add_f32x2(pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
         const uint64_t b1 = add_f32x2(pack_f32x2(fu[k], fu[k + 1]), c1s2);
         const uint64_t b2 = add_f32x2(pack_f32x2(fvs[k], fvs[k + 1]), c2s2);
         float d0, d1, r0, r1;
@@ -296,7 +315,7 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
         float v0, v1;
         unpack_f32x2(mul_f32x2(mul_f32x2(a1, a2), pack_f32x2(r0, r1)), v0, v1);
-        s4 += own[k] ? v0 : 0.f;
+        if (k == 0) s4 = own[0] ? v0 : 0.f; else s4 += own[k] ? v0 : 0.f;
         s4 += own[k + 1] ? v1 : 0.f;
       }
       acc += (double)s4;
@@ -309,22 +328,24 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
     // rows [y0, y0+6) fill the window; [y0+6, sse_end) are complete rows this warp also owns for the squared
     // error; [sse_end, y0+rows_in) are the six rows that belong to the next band's squared error
     const int win_end = y0 + rows_in, sse_end = min(sse_r1, win_end);
-    wa = ldrow(ga, y0); wb = ldrow(gb, y0);
+    wa = __ldg(ga4 + (int64_t)y0 * pitch4);
+    wb = __ldg(gb4 + (int64_t)y0 * pitch4);
     int r = y0;
 #pragma unroll 1
-    for (; r < y0 + 6; ++r) row_step(r, F{}, T{});
+    for (; r < y0 + 6; ++r) row_step(F{}, T{});
 #pragma unroll 1
-    for (; r < sse_end; ++r) row_step(r, T{}, T{});
+    for (; r < sse_end; ++r) row_step(T{}, T{});
 #pragma unroll 1
-    for (; r < win_end; ++r) row_step(r, T{}, F{});
-  } else if (sse_own) {
+    for (; r < win_end; ++r) row_step(T{}, F{});
+  } else {
     // a band without windows (frames lower than 7 rows): squared error only
     for (int r = y0; r < sse_r1; ++r) {
-      const uint32_t xa = ldrow(ga, r), xb = ldrow(gb, r);
+      const uint32_t xa = __ldg(ga4 + (int64_t)r * pitch4);
+      const uint32_t xb = __ldg(gb4 + (int64_t)r * pitch4);
       sqe = __dp4a(xa, xa, sqe); sqe = __dp4a(xb, xb, sqe); cr = __dp4a(xa, xb, cr);
     }
   }
-  sse += (unsigned long long)sqe - 2ull * cr;
+  if (sse_own) sse += (unsigned long long)sqe - 2ull * cr;
 
   acc = warp_sum(acc);
 #pragma unroll
@@ -380,7 +401,8 @@ static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w,
   FrameLayout L{};
   L.pitch = (w + 3) & ~3;
   L.gstride = (int64_t)align_up((size_t)h * L.pitch, 128);
-  L.gray = c.take<uint8_t>((size_t)nf * L.gstride);
+  // + one spare row: the SSIM warps prefetch the row below their band without a bounds test (the value is never used)
+  L.gray = c.take<uint8_t>((size_t)nf * L.gstride + align_up((size_t)L.pitch, 128));
   L.minmax = c.take<int2>((size_t)nf);
   const int out_rows = h >= 7 ? h - 6 : 0, out_cols = w >= 7 ? w - 6 : 0;
   L.bh = kSsimBand;
