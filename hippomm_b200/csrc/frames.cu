@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
 }
 
 // General path (1 channel, odd sizes, padded rows): grid (blocks_per_frame, nf), one byte per thread and step.
+// cpl 7: a row is stored as groups of 7 pixels in 8 bytes (byte 7 of a group and the pixels beyond the row are 0).
 __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restrict__ frames, int64_t npix,
-                                                          int w, int pitch, int ch, uint8_t* __restrict__ gray,
+                                                          int w, int pitch, int ch, int cpl, uint8_t* __restrict__ gray,
                                                           int64_t gstride, int2* __restrict__ minmax) {
   __shared__ uint32_t s_lo[8], s_hi[8];
   const int f = blockIdx.y;
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restr
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < gpix;
        o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = o / pitch;
-    const int x = (int)(o - r * pitch);
-    if (x >= w) { dst[o] = 0; continue; }   // row padding: zero in both frames of a pair
+    const int xb = (int)(o - r * pitch);
+    const int x = cpl == 7 ? (xb >> 3) * 7 + (xb & 7) : xb;
+    if (x >= w || (cpl == 7 && (xb & 7) == 7)) { dst[o] = 0; continue; }   // padding: zero in both frames of a pair
     const int64_t i = r * w + x;
     uint32_t y;
     if (ch == 3) y = bgr2gray(src[i * 3], src[i * 3 + 1], src[i * 3 + 2]);
@@ -134,6 +136,63 @@ __global__ void __launch_bounds__(256) gray_minmax_kernel(const uint8_t* __restr
   }
 }
 
+// 3-channel fast path of the 7-in-8 layout (frame width a multiple of 7, whole warp items): a warp takes 32 runs of 14
+// pixels = 1,344 contiguous BGR bytes, staged like above; a lane's 42 bytes start on a 2-byte boundary for odd lanes,
+// so it reads 12 words and realigns them with funnel shifts, then stores two groups (16 bytes) at once.
+__global__ void __launch_bounds__(256) gray_minmax_vec7_kernel(const uint8_t* __restrict__ frames, int64_t npix,
+                                                               int nf, uint8_t* __restrict__ gray, int64_t gstride,
+                                                               int2* __restrict__ minmax) {
+  __shared__ uint4 s_stage[8][85];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wpf = npix / (14 * 32);                      // warp items per frame
+  const int64_t nitems = wpf * nf;
+  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < nitems; item += (int64_t)gridDim.x * 8) {
+    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;                // first 14-pixel run of the item
+    const uint4* p = reinterpret_cast<const uint4*>(frames + f * npix * 3 + g0 * 42);
+    uint4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) v[u] = ldg_stream(p + lane + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) s_stage[warp][lane + 32 * u] = v[u];
+    __syncwarp();
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_stage[warp]) + (42 * lane >> 2);
+    const uint32_t sh = (lane & 1) * 16;
+    uint32_t raw[12], a[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) raw[i] = sw[i];             // the last word of lane 31 is the slot's spare vector
+#pragma unroll
+    for (int i = 0; i < 11; ++i) a[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+    a[11] = 0u;
+    uint32_t lo = 255, hi = 0, out[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        if ((o & 1) && px == 3) continue;                    // byte 7 of a group stays 0
+        const int q = (o >> 1) * 7 + (o & 1) * 4 + px;       // pixel of the run
+        const int byte0 = q * 3;
+        const uint32_t bgr = __byte_perm(a[byte0 >> 2], a[(byte0 >> 2) + 1], 0x3210 + 0x1111 * (byte0 & 3));
+        const uint32_t y = (uint32_t)__dp2a_hi(kGrayW_R, bgr, __dp2a_lo(kGrayW_BG, bgr, 16384u)) >> 15;
+        lo = min(lo, y); hi = max(hi, y);
+        packed |= y << (px * 8);
+      }
+      out[o] = packed;
+    }
+    *reinterpret_cast<uint4*>(gray + f * gstride + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(&minmax[f].x, (int)lo);
+      atomicMax(&minmax[f].y, (int)hi);
+    }
+  }
+}
+
 __global__ void minmax_init_kernel(int2* minmax, int nf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nf) minmax[i] = make_int2(255, 0);
@@ -141,7 +200,6 @@ __global__ void minmax_init_kernel(int2* minmax, int nf) {
 
 constexpr int kSsimThreads = 256;
 constexpr int kSsimWarps = kSsimThreads / 32;
-constexpr int kSsimChunk = 120;                // output columns owned by a warp (30 lanes x 4)
 constexpr int kSsimLiveSmem = 8 * 1024;        // see frames_adjacent_live_launch
 constexpr int kSsimBand = 56;                  // window rows per band (6 halo rows per band: 11%; 112-row bands measured
                                                // slower on one stream-hour: fewer, longer warp items, longer tail)
@@ -163,8 +221,15 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 | k); }
 
 // One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
-// squared error of image rows [k*bh, ...) (last band: through h); chunk c owns output columns
-// [120c, 120c+120) and reads gray words [30c, 30c+32) of every row.
+// squared error of image rows [k*bh, ...) (last band: through h).  Two gray layouts / lane mappings (`cpl`, columns
+// per lane; frame_layout picks the one that wastes fewer lane slots for the frame width):
+//   cpl 4   rows as they are (pitch = w rounded up to 4): a lane owns one 32-bit word per row, a chunk is 30 lanes =
+//           120 window columns, lanes 30 / 31 only feed their column sums to the windows of lanes 28 / 29;
+//   cpl 7   rows stored as groups of 7 pixels in 8 bytes (byte 7 of a group is 0): a lane owns one group = one 8-byte
+//           load per row, a window spans its own and the next lane's columns only, so a chunk is 31 lanes = 217 window
+//           columns -- and the last lane's first window lies in its own group, which makes a 224-pixel row (218
+//           windows, 32 groups) exactly ONE warp: 97% of the lane slots carry a window, against 85% with two
+//           120-column chunks.
 struct SsimArgs {
   const uint8_t* gray; int64_t gstride; int h, w, pitch;
   const int32_t* pair_a; const int32_t* pair_b;
@@ -177,16 +242,28 @@ struct SsimArgs {
   unsigned int* pair_done; double* out_ssim; double* out_mse;
 };
 
+constexpr int ssim_chunk_cols(int cpl) { return cpl == 7 ? 217 : 120; }
+// chunks per row: cpl 7 lets the last chunk own one window more (the last lane's first)
+__host__ __device__ inline int ssim_nchunks(int out_cols, int cpl) {
+  if (out_cols <= 0) return 1;
+  const int n = cpl == 7 ? (out_cols - 1 + 216) / 217 : (out_cols + 119) / 120;
+  return n < 1 ? 1 : n;
+}
+
 // One (pair, band, chunk) item, by one warp; `item` numbers the items of ALL pairs (pair-major), `slot` is where its
 // partial sums go.
 //
-// Instruction budget of a row step (the kernel is issue / latency bound): the four row words come through
+// Instruction budget of a row step (the kernel is issue / latency bound): the row words come through
 // four running pointers (no per-row index arithmetic, no bounds test: lanes beyond the row read the row's first word, the
 // last step reads one row past the band -- the workspace carries a spare row -- and nothing such a value feeds is owned);
 // per column ONE byte permute yields (x, y, y, x) and a second its zero-extended halves x | y << 16, so that
 // x^2 + y^2 and 2 x y are one dp2a each and sum x | sum y << 16 advances by the difference of two permutes; the squared
 // error is accumulated by every lane and dropped at the end by the lanes that do not own their word.
+template <int CPL>
 __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64_t slot, int lane) {
+  static_assert(CPL == 4 || CPL == 7, "columns per lane");
+  constexpr int W = CPL == 7 ? 2 : 1;                        // 32-bit words a lane loads per row and frame
+  constexpr int kOwnLanes = CPL == 7 ? 31 : 30;              // lanes whose windows belong to the chunk
   const uint8_t* __restrict__ gray = A.gray;
   const int h = A.h, w = A.w, pitch = A.pitch, bh = A.bh, nbands = A.nbands, nchunks = A.nchunks;
   const int32_t* __restrict__ pair_a = A.pair_a;
@@ -199,7 +276,7 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   const int fa = pair_a ? pair_a[p] : p + 1;
   const int fb = pair_b ? pair_b[p] : p;
   const int64_t gpix = A.gstride;
-  const int wordx = (chunk * 30 + lane) * 4;                 // byte offset of this lane's word in a row
+  const int wordx = (chunk * kOwnLanes + lane) * 4 * W;      // byte offset of this lane's word(s) in a row
   const bool col_ok = wordx < pitch;
   const int wordx_ld = col_ok ? wordx : 0;                   // what a lane beyond the row reads instead (never owned)
   const uint8_t* ga = gray + (int64_t)fa * gpix + wordx_ld;
@@ -218,15 +295,22 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   const int y1 = min(y0 + bh, out_rows);          // window-top rows [y0, y1)
   const int rows_in = (y1 > y0) ? (y1 - y0 + 6) : 0;
   const int sse_r1 = (band == nbands - 1) ? h : min(y0 + bh, h);
-  // every image word is counted for the squared error by exactly one warp: chunks overlap by two words
-  const bool sse_own = col_ok && (lane < 30 || chunk == nchunks - 1);
-  // which of this lane's four windows exist and belong to this chunk
-  bool own[4];
+  // every image word is counted for the squared error by exactly one warp (chunks overlap by the feeding lanes); which
+  // of this lane's windows exist and belong to this chunk
+  const bool last_chunk = chunk == nchunks - 1;
+  const bool sse_own = col_ok && (lane < kOwnLanes || last_chunk);
+  const int col0 = (chunk * kOwnLanes + lane) * CPL;          // image column of this lane's first pixel
+  bool own[CPL];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) own[k] = lane < 30 && chunk * kSsimChunk + lane * 4 + k < out_cols;
+  for (int k = 0; k < CPL; ++k) {
+    if constexpr (CPL == 7) own[k] = (lane < kOwnLanes || (k == 0 && last_chunk)) && col0 + k < out_cols;
+    else own[k] = lane < kOwnLanes && col0 + k < out_cols;
+  }
 
   // sliding 7-row column sums: sum x | sum y << 16, sum (x^2 + y^2) (the two variances only ever appear added), 2 sum x y
-  uint32_t sp[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
+  uint32_t sp[CPL], sq[CPL], sxy[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) sp[k] = sq[k] = sxy[k] = 0;
   double acc = 0.0;
   unsigned long long sse = 0;
   uint32_t sqe = 0, cr = 0;                       // sum a^2 + b^2, sum a b of the rows owned for the squared error
@@ -235,37 +319,50 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   // One row step.  kFull: the row completes a 7-row window (horizontal sums + ratio) and the row that leaves the
   // window is fetched for the next step; kSse: this warp owns the row for the squared error.  The phases below
   // call it with compile-time flags, so the steady state carries no per-row predicates.
-  static_assert(kSsimBand + 6 <= 4096, "sqe / cr hold rows x 4 bytes x 2 x 255^2 < 2^32 without a flush: at most 8,256 rows");
-  const int pitch4 = pitch >> 2;                             // words per row (the pitch is a multiple of 4)
-  const uint32_t* ga4 = reinterpret_cast<const uint32_t*>(ga);
-  const uint32_t* gb4 = reinterpret_cast<const uint32_t*>(gb);
-  const uint32_t* pna = ga4 + (int64_t)(y0 + 1) * pitch4;    // the next row of either frame
-  const uint32_t* pnb = gb4 + (int64_t)(y0 + 1) * pitch4;
-  const uint32_t* poa = ga4 + (int64_t)y0 * pitch4;          // the next row to leave the window
-  const uint32_t* pob = gb4 + (int64_t)y0 * pitch4;
+  static_assert(kSsimBand + 6 <= 2048, "sqe / cr hold rows x 8 bytes x 2 x 255^2 < 2^32 without a flush: at most 4,128 rows");
+  using Row = std::conditional_t<W == 2, uint2, uint32_t>;
+  const int pitchw = pitch / (4 * W);                        // row stride in loads (the pitch is a multiple of 4 W)
+  const Row* ga4 = reinterpret_cast<const Row*>(ga);
+  const Row* gb4 = reinterpret_cast<const Row*>(gb);
+  const Row* pna = ga4 + (int64_t)(y0 + 1) * pitchw;         // the next row of either frame
+  const Row* pnb = gb4 + (int64_t)(y0 + 1) * pitchw;
+  const Row* poa = ga4 + (int64_t)y0 * pitchw;               // the next row to leave the window
+  const Row* pob = gb4 + (int64_t)y0 * pitchw;
   // four independent running pointers, one 64-bit multiply-add each per row (left to itself the compiler folds them
   // into two running offsets and re-adds the bases for every load)
   asm("" : "+l"(pna)); asm("" : "+l"(pnb)); asm("" : "+l"(poa)); asm("" : "+l"(pob));
-  uint32_t wa = 0, wb = 0, oa = 0, ob = 0;
+  auto ld = [](const Row* q, uint32_t (&o)[W]) {
+    const Row v = __ldg(q);
+    if constexpr (W == 2) { o[0] = v.x; o[1] = v.y; } else { o[0] = v; }
+  };
+  uint32_t wa[W], wb[W], oa[W], ob[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) wa[i] = wb[i] = oa[i] = ob[i] = 0;
   auto row_step = [&](auto full_tag, auto sse_tag) {
     constexpr bool kFull = decltype(full_tag)::value, kSse = decltype(sse_tag)::value;
     // next row's words (and the row leaving the window): issued now, used in the next step
-    const uint32_t nwa = __ldg(pna), nwb = __ldg(pnb);
-    pna += pitch4; pnb += pitch4;
-    uint32_t noa = 0, nob = 0;
-    if constexpr (kFull) {
-      noa = __ldg(poa); nob = __ldg(pob);
-      poa += pitch4; pob += pitch4;
-    }
-    if constexpr (kSse) { sqe = __dp4a(wa, wa, sqe); sqe = __dp4a(wb, wb, sqe); cr = __dp4a(wa, wb, cr); }
+    uint32_t nwa[W], nwb[W], noa[W], nob[W];
+    ld(pna, nwa); ld(pnb, nwb);
+    pna += pitchw; pnb += pitchw;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t sel = (uint32_t)(k | ((4 + k) << 4) | ((4 + k) << 8) | (k << 12));
-      const uint32_t bn = __byte_perm(wa, wb, sel), hn = __byte_perm(bn, 0u, 0x4140);   // bytes (x, y, y, x); halves x | y << 16
+    for (int i = 0; i < W; ++i) noa[i] = nob[i] = 0;
+    if constexpr (kFull) {
+      ld(poa, noa); ld(pob, nob);
+      poa += pitchw; pob += pitchw;
+    }
+    if constexpr (kSse) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) { sqe = __dp4a(wa[i], wa[i], sqe); sqe = __dp4a(wb[i], wb[i], sqe); cr = __dp4a(wa[i], wb[i], cr); }
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int kk = k & 3, wi = k >> 2;
+      const uint32_t sel = (uint32_t)(kk | ((4 + kk) << 4) | ((4 + kk) << 8) | (kk << 12));
+      const uint32_t bn = __byte_perm(wa[wi], wb[wi], sel), hn = __byte_perm(bn, 0u, 0x4140);   // bytes (x, y, y, x); halves x | y << 16
       sq[k] = __dp2a_lo(hn, bn, sq[k]);            // + x^2 + y^2
       sxy[k] = __dp2a_hi(hn, bn, sxy[k]);          // + 2 x y
       if constexpr (kFull) {
-        const uint32_t bo = __byte_perm(oa, ob, sel), ho = __byte_perm(bo, 0u, 0x4140);
+        const uint32_t bo = __byte_perm(oa[wi], ob[wi], sel), ho = __byte_perm(bo, 0u, 0x4140);
         sq[k] -= __dp2a_lo(ho, bo, 0u);
         sxy[k] -= __dp2a_hi(ho, bo, 0u);
         sp[k] += hn - ho;                          // the running sums never go negative
@@ -274,24 +371,33 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
       }
     }
     if constexpr (kFull) {
-      // prefixes over this lane's four columns; the window starting at column k spans columns k .. k+6:
-      // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the next lane
-      int o_sp[4], o_sq[4], o_xy[4];
-      auto horiz = [&](const uint32_t (&c)[4], int (&o)[4]) {
-        // o[k] = sum of columns k .. k+6: a sliding chain, one 3-input add per window
-        const int c0 = (int)c[0], c1 = (int)c[1], c2 = (int)c[2], c3 = (int)c[3];
-        const int C = c0 + c1 + c2, D = C + c3;
-        const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c3, 1);
-        const int m0 = __shfl_down_sync(0xffffffffu, c0, 2), m1 = __shfl_down_sync(0xffffffffu, c1, 2);
-        o[0] = D + C1n;
-        o[1] = o[0] + n3 - c0;
-        o[2] = o[1] + m0 - c1;
-        o[3] = o[2] + m1 - c2;
+      // o[k] = sum of columns k .. k+6 of a quantity: a sliding chain, one 3-input add per window
+      int o_sp[CPL], o_sq[CPL], o_xy[CPL];
+      auto horiz = [&](const uint32_t (&cu)[CPL], int (&o)[CPL]) {
+        if constexpr (CPL == 4) {
+          // the rest of this lane's columns, then the neighbour's prefix, then one or two columns of the lane after it
+          const int c0 = (int)cu[0], c1 = (int)cu[1], c2 = (int)cu[2], c3 = (int)cu[3];
+          const int C = c0 + c1 + c2, D = C + c3;
+          const int C1n = __shfl_down_sync(0xffffffffu, C, 1), n3 = __shfl_down_sync(0xffffffffu, c3, 1);
+          const int m0 = __shfl_down_sync(0xffffffffu, c0, 2), m1 = __shfl_down_sync(0xffffffffu, c1, 2);
+          o[0] = D + C1n;
+          o[1] = o[0] + n3 - c0;
+          o[2] = o[1] + m0 - c1;
+          o[3] = o[2] + m1 - c2;
+        } else {
+          // window 0 is this lane's own group; window k trades columns 0 .. k-1 for the same columns of the next lane
+          int c[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) c[k] = (int)cu[k];
+          o[0] = ((c[0] + c[1] + c[2]) + (c[3] + c[4] + c[5])) + c[6];
+#pragma unroll
+          for (int k = 1; k < 7; ++k) o[k] = o[k - 1] + __shfl_down_sync(0xffffffffu, c[k - 1], 1) - c[k - 1];
+        }
       };
       horiz(sp, o_sp); horiz(sq, o_sq); horiz(sxy, o_xy);
-      float fu[4], fvs[4], fpxy[4], fvxy[4];
+      float fu[CPL + 1], fvs[CPL + 1], fpxy[CPL + 1], fvxy[CPL + 1];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < CPL; ++k) {
         const int sx = o_sp[k] & 0xffff, sy = (int)((uint32_t)o_sp[k] >> 16);
         const int pxy2 = sx * (sy + sy);                    // 2 * 49^2 mu_x mu_y
         const int u = sy * sy + sx * sx;                    // 49^2 (mu_x^2 + mu_y^2)
@@ -300,11 +406,12 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
         fpxy[k] = (float)pxy2;
         fvxy[k] = (float)(49 * o_xy[k] - pxy2);             // 2 * 48*49 cov_xy, exact
       }
+      fu[CPL] = fu[CPL - 1]; fvs[CPL] = fvs[CPL - 1]; fpxy[CPL] = fpxy[CPL - 1]; fvxy[CPL] = fvxy[CPL - 1];   // odd CPL: pad the last pair
       // the fp32 ratio, two windows per instruction (f32x2: same IEEE results as the scalar forms; the doubled
       // integers convert to exactly twice the fp32 values, so `x2 + c` rounds like fma(2, x, c))
       float s4 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; k += 2) {
+      for (int k = 0; k < CPL; k += 2) {
         const uint64_t a1 = add_f32x2(pack_f32x2(fpxy[k], fpxy[k + 1]), c1s2);
         const uint64_t a2 = add_f32x2(pack_f32x2(fvxy[k], fvxy[k + 1]), c2s2);
         const uint64_t b1 = add_f32x2(pack_f32x2(fu[k], fu[k + 1]), c1s2);
@@ -316,11 +423,12 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
         float v0, v1;
         unpack_f32x2(mul_f32x2(mul_f32x2(a1, a2), pack_f32x2(r0, r1)), v0, v1);
         if (k == 0) s4 = own[0] ? v0 : 0.f; else s4 += own[k] ? v0 : 0.f;
-        s4 += own[k + 1] ? v1 : 0.f;
+        if (k + 1 < CPL) s4 += own[k + 1 < CPL ? k + 1 : k] ? v1 : 0.f;
       }
       acc += (double)s4;
     }
-    wa = nwa; wb = nwb; oa = noa; ob = nob;
+#pragma unroll
+    for (int i = 0; i < W; ++i) { wa[i] = nwa[i]; wb[i] = nwb[i]; oa[i] = noa[i]; ob[i] = nob[i]; }
   };
   using T = std::true_type;
   using F = std::false_type;
@@ -328,8 +436,8 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
     // rows [y0, y0+6) fill the window; [y0+6, sse_end) are complete rows this warp also owns for the squared
     // error; [sse_end, y0+rows_in) are the six rows that belong to the next band's squared error
     const int win_end = y0 + rows_in, sse_end = min(sse_r1, win_end);
-    wa = __ldg(ga4 + (int64_t)y0 * pitch4);
-    wb = __ldg(gb4 + (int64_t)y0 * pitch4);
+    ld(ga4 + (int64_t)y0 * pitchw, wa);
+    ld(gb4 + (int64_t)y0 * pitchw, wb);
     int r = y0;
 #pragma unroll 1
     for (; r < y0 + 6; ++r) row_step(F{}, T{});
@@ -340,9 +448,11 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
   } else {
     // a band without windows (frames lower than 7 rows): squared error only
     for (int r = y0; r < sse_r1; ++r) {
-      const uint32_t xa = __ldg(ga4 + (int64_t)r * pitch4);
-      const uint32_t xb = __ldg(gb4 + (int64_t)r * pitch4);
-      sqe = __dp4a(xa, xa, sqe); sqe = __dp4a(xb, xb, sqe); cr = __dp4a(xa, xb, cr);
+      uint32_t xa[W], xb[W];
+      ld(ga4 + (int64_t)r * pitchw, xa);
+      ld(gb4 + (int64_t)r * pitchw, xb);
+#pragma unroll
+      for (int i = 0; i < W; ++i) { sqe = __dp4a(xa[i], xa[i], sqe); sqe = __dp4a(xb[i], xb[i], sqe); cr = __dp4a(xa[i], xb[i], cr); }
     }
   }
   if (sse_own) sse += (unsigned long long)sqe - 2ull * cr;
@@ -371,11 +481,20 @@ __device__ __forceinline__ void ssim_item(const SsimArgs& A, int64_t item, int64
 }
 
 // One warp per item: warp i of the grid takes item item0 + i (explicit pair lists: pre-filter chain, QA de-dup).
-// Four CTAs per SM (64 registers, no spill).
+// cpl 4: four CTAs of 256 threads per SM (64 registers, no spill); cpl 7: 21 column sums per lane, five CTAs of 128
+// threads at 96 registers (six at 80 registers spill and measured 2% slower; 28-row bands: SSIM 1% slower, a batch of
+// streams 2.5% slower, a single stream 3% faster -- its boundary chain trails a shorter last wave of pairs).
 __global__ void __launch_bounds__(kSsimThreads, 4) ssim_pair_kernel(const SsimArgs A, int64_t nitems, int64_t item0) {
   const int64_t i = (int64_t)blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
   if (i >= nitems) return;
-  ssim_item(A, item0 + i, i, threadIdx.x & 31);
+  ssim_item<4>(A, item0 + i, i, threadIdx.x & 31);
+}
+constexpr int kSsim7Threads = 128;
+constexpr int kSsim7Warps = kSsim7Threads / 32;
+__global__ void __launch_bounds__(kSsim7Threads, 5) ssim_pair7_kernel(const SsimArgs A, int64_t nitems, int64_t item0) {
+  const int64_t i = (int64_t)blockIdx.x * kSsim7Warps + (threadIdx.x >> 5);
+  if (i >= nitems) return;
+  ssim_item<7>(A, item0 + i, i, threadIdx.x & 31);
 }
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
@@ -394,12 +513,23 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ part_ssim,
 
 struct FrameLayout {
   uint8_t* gray; int2* minmax; double* part_ssim; unsigned long long* part_sse;
-  int pitch, bh, nbands, nchunks, nparts; int64_t gstride; size_t bytes;
+  int cpl, pitch, bh, nbands, nchunks, nparts; int64_t gstride; size_t bytes;
 };
+// columns per lane of the SSIM kernel = layout of the gray rows: the mapping that issues fewer row steps x instructions
+// for this width (173 instructions per row step of a 120-column chunk, 290 per 217-column chunk); HIPPO_SSIM_CPL
+// overrides (4 / 7, A/B and tests)
+static int ssim_pick_cpl(int w) {
+  static const int forced = getenv("HIPPO_SSIM_CPL") ? atoi(getenv("HIPPO_SSIM_CPL")) : 0;
+  if (forced == 4 || forced == 7) return forced;
+  if (w < 7) return 4;
+  const int out_cols = w - 6;
+  return ssim_nchunks(out_cols, 7) * 290 < ssim_nchunks(out_cols, 4) * 173 ? 7 : 4;
+}
 static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int npairs) {
   Carver c(ws, ws_bytes);
   FrameLayout L{};
-  L.pitch = (w + 3) & ~3;
+  L.cpl = ssim_pick_cpl(w);
+  L.pitch = L.cpl == 7 ? (w + 6) / 7 * 8 : (w + 3) & ~3;
   L.gstride = (int64_t)align_up((size_t)h * L.pitch, 128);
   // + one spare row: the SSIM warps prefetch the row below their band without a bounds test (the value is never used)
   L.gray = c.take<uint8_t>((size_t)nf * L.gstride + align_up((size_t)L.pitch, 128));
@@ -407,7 +537,7 @@ static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w,
   const int out_rows = h >= 7 ? h - 6 : 0, out_cols = w >= 7 ? w - 6 : 0;
   L.bh = kSsimBand;
   L.nbands = out_rows > 0 ? (out_rows + L.bh - 1) / L.bh : 1;
-  L.nchunks = out_cols > 0 ? (out_cols + kSsimChunk - 1) / kSsimChunk : 1;
+  L.nchunks = ssim_nchunks(out_cols, L.cpl);
   L.nparts = L.nbands * L.nchunks;
   L.part_ssim = c.take<double>((size_t)npairs * L.nparts);
   L.part_sse = c.take<unsigned long long>((size_t)npairs * L.nparts);
@@ -422,14 +552,28 @@ static void gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, con
   int bpf = (int)((npix / 16 + 255) / 256);
   if (bpf < 1) bpf = 1;
   if (bpf > 64) bpf = 64;
-  const bool vec = ch == 3 && L.pitch == w && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
-  if (vec) {
+  const bool aligned = ch == 3 && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (aligned && L.cpl == 4 && L.pitch == w) {
     const int64_t items = (npix / 16 + 31) / 32 * nf;
-    const int64_t want = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
+    const int64_t want = (items + 7) / 8;
     gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.gstride, L.minmax);
+  } else if (aligned && L.cpl == 7 && w % 7 == 0 && npix % (14 * 32) == 0) {
+    // rows are whole groups, so the frame is one run of groups: 14 pixels (two groups, 16 gray bytes) per lane
+    const int64_t items = npix / (14 * 32) * nf;
+    const int64_t want = (items + 7) / 8;
+    gray_minmax_vec7_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.gstride, L.minmax);
   } else {
-    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.gray, L.gstride, L.minmax);
+    gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.cpl, L.gray, L.gstride, L.minmax);
   }
+}
+
+// the SSIM launch of `nitems` (pair, band, chunk) items for layout L
+static void ssim_launch(const FrameLayout& L, const SsimArgs& A, int64_t nitems, size_t smem, cudaStream_t s) {
+  if (L.cpl == 7)
+    ssim_pair7_kernel<<<(unsigned)((nitems + kSsim7Warps - 1) / kSsim7Warps), kSsim7Threads, smem, s>>>(A, nitems, 0);
+  else
+    ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, smem, s>>>(A, nitems, 0);
 }
 
 // Adjacent pairs [0, nf - 1) of a stream with LIVE finalisation (pattern.cu): gray conversion, then one SSIM launch
@@ -450,7 +594,7 @@ hippo_status frames_adjacent_live_launch(const uint8_t* frames, int nf, int h, i
   const int64_t nitems = (int64_t)npairs * L.nparts;
   const SsimArgs A{L.gray, L.gstride, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, L.bh, L.nbands, L.nchunks,
                    L.part_ssim, L.part_sse, pair_done, out_ssim, out_mse};
-  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, kSsimLiveSmem, s>>>(A, nitems, 0);
+  ssim_launch(L, A, nitems, kSsimLiveSmem, s);
   HIPPO_CUDA(cudaGetLastError());
   return HIPPO_OK;
 }
@@ -490,7 +634,7 @@ hippo_status hippo_frame_pairs(const uint8_t* frames, int32_t nf, int32_t h, int
   const int64_t nitems = (int64_t)npairs * L.nparts;
   const SsimArgs A{L.gray, L.gstride, h, w, L.pitch, pair_a, pair_b, L.minmax, range_mode, L.bh, L.nbands, L.nchunks,
                    L.part_ssim, L.part_sse, nullptr, nullptr, nullptr};
-  ssim_pair_kernel<<<(unsigned)((nitems + kSsimWarps - 1) / kSsimWarps), kSsimThreads, 0, s>>>(A, nitems, 0);
+  ssim_launch(L, A, nitems, 0, s);
   HIPPO_CUDA(cudaGetLastError());
   ssim_finalize_kernel<<<(npairs + 127) / 128, 128, 0, s>>>(L.part_ssim, L.part_sse, npairs, L.nparts, h, w,
                                                            out_ssim, out_mse);

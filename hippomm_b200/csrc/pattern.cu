@@ -151,6 +151,39 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   };
   mark(main, "start");
 
+  // The chain reads the 512-sample sums (0.9 MB per stream-hour) while the frame kernels stream ~0.9 GB through L2:
+  // left alone every such read goes to DRAM behind that traffic and a segment takes ~3 us instead of 1.4.  The pyramid
+  // kernels (aux) and the chain (chain) therefore access the sums with the persisting L2 policy.
+  const char* pin_env = getenv("HIPPO_PATTERN_L2PIN");      // 0 switches it off (A/B)
+  if (follow && has_audio && !(pin_env && atoi(pin_env) == 0)) {
+    static thread_local int l2_ready = 0;            // 0 = not tried, 1 = set-aside configured, -1 = unavailable
+    if (l2_ready == 0) {
+      int dev = 0, max_persist = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      size_t want = (size_t)8 << 20;
+      if ((size_t)max_persist < want) want = (size_t)max_persist;
+      l2_ready = (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) ? 1 : -1;
+      cudaGetLastError();
+    }
+    if (l2_ready == 1) {
+      int dev = 0, max_win = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      size_t bytes = (size_t)((ns + 511) / 512) * sizeof(double);
+      if (bytes > (size_t)max_win) bytes = (size_t)max_win;
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = out_e512;
+      av.accessPolicyWindow.num_bytes = bytes;
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(aux, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaStreamSetAttribute(chain, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaGetLastError();
+    }
+  }
+
   // chain stream: stream descriptor + fresh state (+ pending marks), then the follower at once
   hippo_stream_desc d{};
   d.ssim = scored ? out_ssim : nullptr;

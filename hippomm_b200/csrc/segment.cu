@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
       const unsigned long long t0 = globaltimer_ns();
       for (;;) {
         const bool audio_ok = follow_gate == nullptr || !has_audio || ld_volatile_u32(follow_gate) != 0;
-        const bool video_ok = S.ssim == nullptr || nf < 2 ||
+        // with audio the chain starts at once: most segments are settled by a silent window and never wait for a pair
+        const bool video_ok = S.ssim == nullptr || nf < 2 || (has_audio && follow_gate != nullptr) ||
                               __double_as_longlong(ld_volatile_f64(S.ssim)) != (long long)kSsimPending;
         if (audio_ok && video_ok) break;
         if (globaltimer_ns() - t0 > (unsigned long long)follow_ns) { s_abort = 1; break; }
@@ -297,6 +298,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) segment_kernel(const hippo_str
                 for (;;) {
                   sv = ld_volatile_f64(S.ssim + (i - 1));
                   if (__double_as_longlong(sv) != (long long)kSsimPending) { if (staged) s_stage[kStageFrames + i - 1] = sv; break; }
+                  // a window already KNOWN to be silent settles the segment: the audio boundary overwrites the video
+                  // boundary (hm:1061-1077 run second), so this pair's value cannot matter any more -- stop waiting
+                  // for it (sv stays pending = NaN: no candidate; the pair is polled again if a later segment needs it)
+                  if (scan_audio && *(volatile int*)&s_apick[set] != 0x7fffffff) break;
                   if (globaltimer_ns() - t0 > (unsigned long long)follow_ns) { s_abort = 1; break; }
                   __nanosleep(40);
                 }

@@ -85,9 +85,13 @@ def test_sass_of_the_streaming_kernels_uses_the_intended_instructions():
             pytest.skip(f"{fragment} not found in the ELF listing")
         return m.group(1)
 
-    ssim = sass_of(mangled("ssim_pair_kernel"))
-    for mnemonic in ("FFMA2", "FMUL2", "FADD2", "IDP.4A", "SHFL.DOWN", "MUFU.RCP"):
-        assert mnemonic in ssim, f"{mnemonic} missing from ssim_pair_kernel"
+    for kernel in ("ssim_pair_kernel", "ssim_pair7_kernel"):
+        ssim = sass_of(mangled(kernel))
+        # x^2 + y^2 and 2xy of a column are one 16 x 8-bit dot product each (IDP.2A), the squared error a byte dot
+        # product (IDP.4A), the ratio runs on packed fp32 pairs
+        for mnemonic in ("FMUL2", "FADD2", "IDP.4A", "IDP.2A.LO", "IDP.2A.HI", "SHFL.DOWN", "MUFU.RCP"):
+            assert mnemonic in ssim, f"{mnemonic} missing from {kernel}"
+        assert "LDL" not in ssim and "STL" not in ssim, f"{kernel} spills"
     seg = sass_of(mangled("segment_kernel"))
     assert "REDUX" in seg and "ATOMS.MAX" in seg, "boundary kernel: warp reduce + native shared atomic expected"
     assert "ATOMS.CAST.SPIN.64" not in seg, "boundary kernel: 64-bit compare-and-swap loop is back"
