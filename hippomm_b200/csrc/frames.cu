@@ -68,19 +68,29 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
   const int64_t ngroups = npix / 16;
   const int64_t wpf = (ngroups + 31) / 32;                   // warp items per frame
   const int64_t nitems = wpf * nf;
-  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < nitems; item += (int64_t)gridDim.x * 8) {
-    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;
-    const uint8_t* src = frames + f * npix * 3;
-    uint8_t* dst = gray + f * gstride;
-    const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
+  // the loads of a warp's NEXT item are in flight while it converts the current one (one item at a time left the
+  // warps waiting on HBM for half of their cycles)
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  int64_t item = (int64_t)blockIdx.x * 8 + warp;
+  uint4 v[3];
+  auto issue = [&](int64_t it) {
+    const int64_t f = it / wpf, g0 = (it - f * wpf) * 32;
+    const int64_t left = ngroups - g0;
     const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
-    const uint4* p = reinterpret_cast<const uint4*>(src + g0 * 48);
-    uint4 v[3];
+    const uint4* p = reinterpret_cast<const uint4*>(frames + f * npix * 3 + g0 * 48);
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) v[u] = ldg_stream(p + lane + 32 * u);
+  };
+  if (item < nitems) issue(item);
+  for (; item < nitems; item += stride) {
+    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;
+    uint8_t* dst = gray + f * gstride;
+    const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
+    const int nvec = left >= 32 ? 96 : (int)left * 3;
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
     __syncwarp();
+    if (item + stride < nitems) issue(item + stride);
     uint32_t lo = 255, hi = 0;
     if (lane < left) *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = gray16(s_stage[warp], lane, lo, hi);
     __syncwarp();
@@ -146,15 +156,22 @@ __global__ void __launch_bounds__(256) gray_minmax_vec7_kernel(const uint8_t* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wpf = npix / (14 * 32);                      // warp items per frame
   const int64_t nitems = wpf * nf;
-  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < nitems; item += (int64_t)gridDim.x * 8) {
-    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;                // first 14-pixel run of the item
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  int64_t item = (int64_t)blockIdx.x * 8 + warp;
+  uint4 v[3];
+  auto issue = [&](int64_t it) {                             // the next item's loads fly under this item's conversion
+    const int64_t f = it / wpf, g0 = (it - f * wpf) * 32;
     const uint4* p = reinterpret_cast<const uint4*>(frames + f * npix * 3 + g0 * 42);
-    uint4 v[3];
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) v[u] = ldg_stream(p + lane + 32 * u);
+  };
+  if (item < nitems) issue(item);
+  for (; item < nitems; item += stride) {
+    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;                // first 14-pixel run of the item
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) s_stage[warp][lane + 32 * u] = v[u];
     __syncwarp();
+    if (item + stride < nitems) issue(item + stride);
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_stage[warp]) + (42 * lane >> 2);
     const uint32_t sh = (lane & 1) * 16;
     uint32_t raw[12], a[12];
@@ -546,22 +563,30 @@ static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w,
 }
 
 // gray conversion of all frames (+ min / max), stream s
-static void gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, const FrameLayout& L, cudaStream_t s) {
+// `reserved_sms`: SMs another resident kernel keeps to itself (the boundary chain in follow mode)
+static void gray_launch(const uint8_t* frames, int nf, int h, int w, int ch, const FrameLayout& L, cudaStream_t s,
+                        int reserved_sms = 0) {
   const int64_t npix = (int64_t)h * w;
   minmax_init_kernel<<<(nf + 255) / 256, 256, 0, s>>>(L.minmax, nf);
   int bpf = (int)((npix / 16 + 255) / 256);
   if (bpf < 1) bpf = 1;
   if (bpf > 64) bpf = 64;
   const bool aligned = ch == 3 && npix % 16 == 0 && (((uintptr_t)frames) & 15) == 0;   // L.gray is 256-byte aligned
-  const int64_t cap = (int64_t)sm_count() * 8;
+  // persistent grids: exactly the CTAs that are resident at once (a second, thin wave would run on a mostly idle GPU)
+  auto resident = [reserved_sms](const void* fn, int& cached) -> int64_t {
+    if (cached == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, fn, 256, 0) != cudaSuccess || cached < 1)) cached = 4;
+    const int sms = sm_count() - reserved_sms;
+    return (int64_t)(sms > 1 ? sms : 1) * cached;
+  };
+  static int occ4 = 0, occ7 = 0;
   if (aligned && L.cpl == 4 && L.pitch == w) {
     const int64_t items = (npix / 16 + 31) / 32 * nf;
-    const int64_t want = (items + 7) / 8;
+    const int64_t want = (items + 7) / 8, cap = resident((const void*)gray_minmax_vec_kernel, occ4);
     gray_minmax_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.gstride, L.minmax);
   } else if (aligned && L.cpl == 7 && w % 7 == 0 && npix % (14 * 32) == 0) {
     // rows are whole groups, so the frame is one run of groups: 14 pixels (two groups, 16 gray bytes) per lane
     const int64_t items = npix / (14 * 32) * nf;
-    const int64_t want = (items + 7) / 8;
+    const int64_t want = (items + 7) / 8, cap = resident((const void*)gray_minmax_vec7_kernel, occ7);
     gray_minmax_vec7_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(frames, npix, nf, L.gray, L.gstride, L.minmax);
   } else {
     gray_minmax_kernel<<<dim3(bpf, nf), 256, 0, s>>>(frames, npix, w, L.pitch, ch, L.cpl, L.gray, L.gstride, L.minmax);
@@ -589,7 +614,7 @@ hippo_status frames_adjacent_live_launch(const uint8_t* frames, int nf, int h, i
   }
   const int npairs = nf - 1;
   if (npairs <= 0) return HIPPO_OK;
-  gray_launch(frames, nf, h, w, ch, L, s);
+  gray_launch(frames, nf, h, w, ch, L, s, pair_done != nullptr ? 1 : 0);
   HIPPO_CUDA(cudaGetLastError());
   const int64_t nitems = (int64_t)npairs * L.nparts;
   const SsimArgs A{L.gray, L.gstride, h, w, L.pitch, nullptr, nullptr, L.minmax, 0, L.bh, L.nbands, L.nchunks,

@@ -31,10 +31,12 @@ def test_frame_ssim_matches_reference_outputs(cuda_device):
 
 
 @pytest.mark.parametrize("h,w", [(7, 7), (8, 300), (57, 63), (64, 64), (119, 257), (224, 224), (180, 320), (70, 600),
-                                 (62, 126), (63, 127), (9, 247), (118, 246), (61, 13)])
+                                 (62, 126), (63, 127), (9, 247), (118, 246), (61, 13), (20, 223), (15, 225), (30, 441),
+                                 (12, 440), (64, 196), (9, 373)])
 def test_frame_pairs_shapes_against_oracle(cuda_device, h, w):
-    """Frame sizes around the band (56 window rows) and column-chunk (120 windows per warp) boundaries, widths
-    that are / are not multiples of 4 (row padding of the gray buffer) and of 16 (vectorised gray path)."""
+    """Frame sizes around the band (56 window rows) and column-chunk boundaries (120 windows per warp with 4 columns
+    per lane, 217 (+1) with 7: widths 127-224 and 367-441 take the 7-in-8 gray layout), widths that are / are not
+    multiples of 4 or 7 (row padding of the gray buffer) and of 16 / 14 x 32 (vectorised gray paths)."""
     from hippomm_b200 import synth
 
     frames, _ = synth.frame_stream(h * 1000 + w, 6, h, w, min_scene=2, max_scene=3)
@@ -49,6 +51,40 @@ def test_frame_pairs_shapes_against_oracle(cuda_device, h, w):
     gray = np.stack([O.bgr2gray(f) for f in frames])[..., None]
     ssim_g, _ = _ssim_adjacent(np.ascontiguousarray(gray), cuda_device)
     assert np.array_equal(ssim_g, ssim)
+
+
+@pytest.mark.parametrize("cpl", [4, 7])
+def test_frame_pairs_with_either_gray_layout_forced(cuda_device, cpl):
+    """HIPPO_SSIM_CPL forces one lane mapping / gray layout for every width (read once per process, hence the child
+    process): shapes that cross the chunk boundaries of both mappings, each against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from hippomm_b200 import synth\n"
+        "from hippomm_b200.segmentation import frame_pair_scores_device\n"
+        "from oracle import hippo_oracle as O\n"
+        "dev = torch.device('cuda', 0)\n"
+        "for h, w in [(7, 7), (9, 13), (64, 64), (30, 126), (30, 127), (20, 223), (224, 224), (15, 225), (12, 440),\n"
+        "             (30, 441), (9, 442), (70, 600), (180, 320)]:\n"
+        "    frames, _ = synth.frame_stream(h * 1000 + w, 4, h, w, min_scene=2, max_scene=2)\n"
+        "    ssim, mse = frame_pair_scores_device(torch.from_numpy(frames).to(dev), range_mode=0)\n"
+        "    ref = O.adjacent_ssim(frames)\n"
+        "    got = ssim.cpu().numpy()\n"
+        "    assert np.max(np.abs(got - ref)) < 1e-6, (h, w, got, ref)\n"
+        "    for p in range(len(frames) - 1):\n"
+        "        g1 = O.bgr2gray(frames[p + 1]).astype(np.float64) / 255.0\n"
+        "        g0 = O.bgr2gray(frames[p]).astype(np.float64) / 255.0\n"
+        "        assert abs(float(mse[p]) - np.mean((g1 - g0) ** 2)) < 1e-12, (h, w, p)\n"
+        "print('layout ok')\n"
+    )
+    env = dict(os.environ, HIPPO_SSIM_CPL=str(cpl))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "layout ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_frame_similarity_and_difference_wrappers(cuda_device):
