@@ -80,3 +80,17 @@ if dbg:
     os.environ["HIPPO_SEG_DEBUG"] = dbg
     segment_boundaries_device(ssim, ft, pcm, pyr, sr, 30.0, 10.0, 0.95, -40.0, 512)
     torch.cuda.synchronize()
+if os.environ.get("HOSTTIME"):
+    import time
+    nb = int(os.environ["HOSTTIME"])
+    for mode, lanes in (("stages", 3), ("stages", 1), ("pipeline", 2)):
+        for _ in range(2):
+            pattern_separation_batch_device([(frames, ft, pcm, sr)] * nb, 30.0, 10.0, 0.95, -40.0, 512, lanes=lanes, mode=mode)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pattern_separation_batch_device([(frames, ft, pcm, sr)] * nb, 30.0, 10.0, 0.95, -40.0, 512, lanes=lanes, mode=mode)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"[seg_only] host issue time, batch of {nb}, {mode}, {lanes} lanes: {(t1 - t0) / nb * 1e3:.3f} ms per stream issued, "
+              f"{(t2 - t0) / nb * 1e3:.3f} ms per stream until the GPU is done")
