@@ -68,41 +68,52 @@ __global__ void __launch_bounds__(256) gray_minmax_vec_kernel(const uint8_t* __r
   const int64_t ngroups = npix / 16;
   const int64_t wpf = (ngroups + 31) / 32;                   // warp items per frame
   const int64_t nitems = wpf * nf;
-  // the loads of a warp's NEXT item are in flight while it converts the current one (one item at a time left the
-  // warps waiting on HBM for half of their cycles)
-  const int64_t stride = (int64_t)gridDim.x * 8;
-  int64_t item = (int64_t)blockIdx.x * 8 + warp;
+  // Every warp takes a CONTIGUOUS run of items (no division per item, and the frame's min / max is reduced across the
+  // warp once per frame instead of once per item); the loads of its NEXT item are in flight while it converts the
+  // current one (one item at a time left the warps waiting on HBM for half of their cycles).
+  const int64_t nwarps = (int64_t)gridDim.x * 8, wid = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t per = (nitems + nwarps - 1) / nwarps;
+  int64_t item = wid * per;
+  const int64_t item_end = item + per < nitems ? item + per : nitems;
+  if (item >= item_end) return;
+  int64_t f = item / wpf;
+  int64_t j = item - f * wpf;                                // item of the frame
   uint4 v[3];
-  auto issue = [&](int64_t it) {
-    const int64_t f = it / wpf, g0 = (it - f * wpf) * 32;
-    const int64_t left = ngroups - g0;
+  auto issue = [&](int64_t fi, int64_t ji) {
+    const int64_t g0 = ji * 32, left = ngroups - g0;
     const int nvec = left >= 32 ? 96 : (int)left * 3;        // 16-byte vectors to stage
-    const uint4* p = reinterpret_cast<const uint4*>(frames + f * npix * 3 + g0 * 48);
+    const uint4* p = reinterpret_cast<const uint4*>(frames + fi * npix * 3 + g0 * 48);
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) v[u] = ldg_stream(p + lane + 32 * u);
   };
-  if (item < nitems) issue(item);
-  for (; item < nitems; item += stride) {
-    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;
+  issue(f, j);
+  uint32_t lo = 255, hi = 0;
+  for (; item < item_end; ++item) {
+    const int64_t g0 = j * 32;
     uint8_t* dst = gray + f * gstride;
     const int64_t left = ngroups - g0;                       // groups this warp still has: >= 1
     const int nvec = left >= 32 ? 96 : (int)left * 3;
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < nvec) s_stage[warp][lane + 32 * u] = v[u];
     __syncwarp();
-    if (item + stride < nitems) issue(item + stride);
-    uint32_t lo = 255, hi = 0;
+    const bool frame_ends = j + 1 == wpf;
+    const int64_t fn = frame_ends ? f + 1 : f, jn = frame_ends ? 0 : j + 1;
+    if (item + 1 < item_end) issue(fn, jn);
     if (lane < left) *reinterpret_cast<uint4*>(dst + (g0 + lane) * 16) = gray16(s_stage[warp], lane, lo, hi);
     __syncwarp();
+    if (frame_ends || item + 1 == item_end) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (lane == 0) {
+        atomicMin(&minmax[f].x, (int)lo);
+        atomicMax(&minmax[f].y, (int)hi);
+      }
+      lo = 255; hi = 0;
     }
-    if (lane == 0) {
-      atomicMin(&minmax[f].x, (int)lo);
-      atomicMax(&minmax[f].y, (int)hi);
-    }
+    f = fn; j = jn;
   }
 }
 
@@ -156,22 +167,31 @@ __global__ void __launch_bounds__(256) gray_minmax_vec7_kernel(const uint8_t* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wpf = npix / (14 * 32);                      // warp items per frame
   const int64_t nitems = wpf * nf;
-  const int64_t stride = (int64_t)gridDim.x * 8;
-  int64_t item = (int64_t)blockIdx.x * 8 + warp;
+  // contiguous run of items per warp, next item's loads in flight under the conversion, min / max reduced once per
+  // frame (see gray_minmax_vec_kernel)
+  const int64_t nwarps = (int64_t)gridDim.x * 8, wid = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t per = (nitems + nwarps - 1) / nwarps;
+  int64_t item = wid * per;
+  const int64_t item_end = item + per < nitems ? item + per : nitems;
+  if (item >= item_end) return;
+  int64_t f = item / wpf;
+  int64_t j = item - f * wpf;
   uint4 v[3];
-  auto issue = [&](int64_t it) {                             // the next item's loads fly under this item's conversion
-    const int64_t f = it / wpf, g0 = (it - f * wpf) * 32;
-    const uint4* p = reinterpret_cast<const uint4*>(frames + f * npix * 3 + g0 * 42);
+  auto issue = [&](int64_t fi, int64_t ji) {
+    const uint4* p = reinterpret_cast<const uint4*>(frames + fi * npix * 3 + ji * (32 * 42));
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) v[u] = ldg_stream(p + lane + 32 * u);
   };
-  if (item < nitems) issue(item);
-  for (; item < nitems; item += stride) {
-    const int64_t f = item / wpf, g0 = (item - f * wpf) * 32;                // first 14-pixel run of the item
+  issue(f, j);
+  uint32_t lo = 255, hi = 0;
+  for (; item < item_end; ++item) {
+    const int64_t g0 = j * 32;                                               // first 14-pixel run of the item
 #pragma unroll
     for (int u = 0; u < 3; ++u) if (lane + 32 * u < 84) s_stage[warp][lane + 32 * u] = v[u];
     __syncwarp();
-    if (item + stride < nitems) issue(item + stride);
+    const bool frame_ends = j + 1 == wpf;
+    const int64_t fn = frame_ends ? f + 1 : f, jn = frame_ends ? 0 : j + 1;
+    if (item + 1 < item_end) issue(fn, jn);
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_stage[warp]) + (42 * lane >> 2);
     const uint32_t sh = (lane & 1) * 16;
     uint32_t raw[12], a[12];
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(256) gray_minmax_vec7_kernel(const uint8_t* __
 #pragma unroll
     for (int i = 0; i < 11; ++i) a[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
     a[11] = 0u;
-    uint32_t lo = 255, hi = 0, out[4];
+    uint32_t out[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       uint32_t packed = 0;
@@ -198,15 +218,19 @@ __global__ void __launch_bounds__(256) gray_minmax_vec7_kernel(const uint8_t* __
     }
     *reinterpret_cast<uint4*>(gray + f * gstride + (g0 + lane) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
     __syncwarp();
+    if (frame_ends || item + 1 == item_end) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (lane == 0) {
+        atomicMin(&minmax[f].x, (int)lo);
+        atomicMax(&minmax[f].y, (int)hi);
+      }
+      lo = 255; hi = 0;
     }
-    if (lane == 0) {
-      atomicMin(&minmax[f].x, (int)lo);
-      atomicMax(&minmax[f].y, (int)hi);
-    }
+    f = fn; j = jn;
   }
 }
 
