@@ -557,19 +557,24 @@ struct FrameLayout {
   int cpl, pitch, bh, nbands, nchunks, nparts; int64_t gstride; size_t bytes;
 };
 // columns per lane of the SSIM kernel = layout of the gray rows: the mapping that issues fewer row steps x instructions
-// for this width (173 instructions per row step of a 120-column chunk, 290 per 217-column chunk); HIPPO_SSIM_CPL
-// overrides (4 / 7, A/B and tests)
-static int ssim_pick_cpl(int w) {
+// for this width (173 instructions per row step of a 120-column chunk, 290 per 217-column chunk) -- unless that would
+// trade the vectorised gray conversion for the byte-wise one (7-in-8 rows are only written by the fast kernel when the
+// width is a multiple of 7 and the frame is whole warp items).  HIPPO_SSIM_CPL overrides (4 / 7, A/B and tests).
+static int ssim_pick_cpl(int h, int w) {
   static const int forced = getenv("HIPPO_SSIM_CPL") ? atoi(getenv("HIPPO_SSIM_CPL")) : 0;
   if (forced == 4 || forced == 7) return forced;
   if (w < 7) return 4;
   const int out_cols = w - 6;
-  return ssim_nchunks(out_cols, 7) * 290 < ssim_nchunks(out_cols, 4) * 173 ? 7 : 4;
+  if (ssim_nchunks(out_cols, 7) * 290 >= ssim_nchunks(out_cols, 4) * 173) return 4;
+  const int64_t npix = (int64_t)h * w;
+  const bool vec7 = w % 7 == 0 && npix % (14 * 32) == 0 && npix % 16 == 0;
+  const bool vec4 = w % 4 == 0 && npix % 16 == 0;
+  return (vec7 || !vec4) ? 7 : 4;
 }
 static FrameLayout frame_layout(void* ws, size_t ws_bytes, int nf, int h, int w, int npairs) {
   Carver c(ws, ws_bytes);
   FrameLayout L{};
-  L.cpl = ssim_pick_cpl(w);
+  L.cpl = ssim_pick_cpl(h, w);
   L.pitch = L.cpl == 7 ? (w + 6) / 7 * 8 : (w + 3) & ~3;
   L.gstride = (int64_t)align_up((size_t)h * L.pitch, 128);
   // + one spare row: the SSIM warps prefetch the row below their band without a bounds test (the value is never used)

@@ -35,7 +35,8 @@ def test_frame_ssim_matches_reference_outputs(cuda_device):
                                  (12, 440), (64, 196), (9, 373)])
 def test_frame_pairs_shapes_against_oracle(cuda_device, h, w):
     """Frame sizes around the band (56 window rows) and column-chunk boundaries (120 windows per warp with 4 columns
-    per lane, 217 (+1) with 7: widths 127-224 and 367-441 take the 7-in-8 gray layout), widths that are / are not
+    per lane, 217 (+1) with 7: widths 127-224 and 367-441 take the 7-in-8 gray layout unless only the 4-column layout has
+    a vectorised gray path for the size), widths that are / are not
     multiples of 4 or 7 (row padding of the gray buffer) and of 16 / 14 x 32 (vectorised gray paths)."""
     from hippomm_b200 import synth
 
