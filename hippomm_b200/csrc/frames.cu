@@ -11,14 +11,15 @@
 // uint8), the variance / covariance numerators 49*Sxx - Sx^2 are formed in int32 with no
 // cancellation error, and only the final ratio is evaluated in fp32.
 //
-//   gray_minmax_kernel : BGR -> gray (cv2's fixed point: (3735 B + 19235 G + 9798 R + 16384) >> 15),
-//                        rows padded with zeros to a multiple of 4 bytes, per-frame min / max (the data
-//                        range of hm:990 is computed in uint8)
-//   ssim_pair_kernel   : one WARP per (pair, band of rows, chunk of 120 columns), no block-level
-//                        synchronisation.  A lane owns 4 adjacent columns (one 32-bit word of each frame
-//                        per row), marches down the rows with sliding 7-row column sums, and gets the
-//                        6 columns to its right from its two neighbours with 16 shuffles of column-sum
-//                        prefixes.  Issue-bound (integer ALU), not HBM-bound: see DESIGN.md.
+//   gray_minmax_*kernel : BGR -> gray (cv2's fixed point: (3735 B + 19235 G + 9798 R + 16384) >> 15), per-frame
+//                         min / max (the data range of hm:990 is computed in uint8).  Two row layouts, one per lane
+//                         mapping of the SSIM kernel: rows padded with zeros to a multiple of 4 bytes, or groups of 7
+//                         pixels in 8 bytes (byte 7 = 0); a vectorised kernel for each (persistent warps, the next
+//                         item's loads in flight under the conversion) and a byte-wise one for odd sizes
+//   ssim_pair*_kernel   : one WARP per (pair, band of rows, chunk of columns), no block-level synchronisation.  A
+//                         lane owns 4 (or 7) adjacent columns, marches down the rows with sliding 7-row column sums
+//                         (x^2 + y^2 and 2xy by dp2a on permuted bytes) and gets the columns to its right from its
+//                         neighbours by shuffles.  Issue-bound (integer ALU), not HBM-bound: see DESIGN.md 4.4.
 //   ssim_finalize_kernel: ordered sum of the warp partials -> mean SSIM, MSE
 #include "common.cuh"
 #include <cstdlib>
@@ -258,8 +259,6 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
-
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 | k); }
 
 // One warp per (pair, band, chunk).  Band k produces SSIM window-top rows [k*bh, min((k+1)*bh, h-6)) and the
 // squared error of image rows [k*bh, ...) (last band: through h).  Two gray layouts / lane mappings (`cpl`, columns
