@@ -153,13 +153,21 @@ def _audio_to_device(audio_data, dev, int16_pcm: bool = False):
     return t.contiguous()
 
 
-def audio_energy_device(pcm: torch.Tensor):
-    """pcm [ns, nch] device tensor -> (e16 fp64 [ceil(ns/16)], e512 fp64 [ceil(ns/512)])."""
+def audio_energy_device(pcm: torch.Tensor, out=None):
+    """pcm [ns, nch] device tensor -> (e16 fp64 [ceil(ns/16)], e512 fp64 [ceil(ns/512)]).
+    `out` = (e16, e512) contiguous fp64 tensors of exactly those sizes to write into."""
     lib = _lib.load()
     dev = _cuda.require_device(pcm.device)
     ns, nch = pcm.shape
-    e16 = torch.empty((max((ns + 15) // 16, 1),), dtype=torch.float64, device=dev)
-    e512 = torch.empty((max((ns + 511) // 512, 1),), dtype=torch.float64, device=dev)
+    n16, n512 = max((ns + 15) // 16, 1), max((ns + 511) // 512, 1)
+    if out is not None:
+        e16, e512 = out
+        if e16.dtype != torch.float64 or e512.dtype != torch.float64 or e16.numel() != n16 or e512.numel() != n512 \
+                or not e16.is_contiguous() or not e512.is_contiguous():
+            raise ValueError("out must be contiguous fp64 tensors of ceil(ns/16) and ceil(ns/512) elements")
+    else:
+        e16 = torch.empty((n16,), dtype=torch.float64, device=dev)
+        e512 = torch.empty((n512,), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.hippo_audio_energy(pcm.data_ptr(), _PCM_ENUM[pcm.dtype], ns, nch, e16.data_ptr(),
                                           e512.data_ptr(), _cuda.stream_ptr()))
@@ -267,20 +275,34 @@ def pattern_separation_batch_device(streams, max_segment_duration: float, min_se
         main = torch.cuda.current_stream()
         if mode == "stages":
             side = _side_streams(dev, lanes)
+            # SSIM values and audio pyramids of all streams (29.7 MB per stream-hour) live in ONE grow-only arena of the
+            # caller's stream until the boundary launch has read them: fresh blocks per stream and call made the
+            # caching allocator fall back to cudaMalloc whenever the previous batch was still in flight
+            layout, total = [], 0
+            for frames, ft, pcm, sr in streams:
+                npairs = frames.shape[0] - 1 if (frames is not None and frames.shape[0] > 1) else 0
+                ns = pcm.shape[0] if pcm is not None else 0
+                n16, n512 = (max((ns + 15) // 16, 1), max((ns + 511) // 512, 1)) if pcm is not None else (0, 0)
+                offs = []
+                for cnt in (npairs, npairs, n16, n512):
+                    offs.append((total, cnt))
+                    total += (cnt + 31) // 32 * 32                      # fp64 elements, 256-byte aligned
+                layout.append(offs)
+            arena = _cuda.workspace(total * 8, dev, "batch_arena").view(torch.float64) if total else None
             for sd in side:
                 sd.wait_stream(main)
             prepared = []
             for i, (frames, ft, pcm, sr) in enumerate(streams):
                 sd = side[i % len(side)]
+                (o_s, n_s), (o_m, n_m), (o_16, n_16), (o_512, n_512) = layout[i]
                 with torch.cuda.stream(sd):
                     ssim = pyr = None
-                    if frames is not None and frames.shape[0] > 1:
-                        ssim, _ = frame_pair_scores_device(frames, range_mode=0)
-                        ssim.record_stream(main)
+                    if n_s > 0:
+                        ssim, _ = frame_pair_scores_device(frames, range_mode=0,
+                                                           out=(arena[o_s:o_s + n_s], arena[o_m:o_m + n_m]))
                     if pcm is not None:
-                        pyr = audio_energy_device(pcm)
-                        pyr[0].record_stream(main)
-                        pyr[1].record_stream(main)
+                        p2 = pcm.reshape(-1, 1) if pcm.dim() == 1 else pcm
+                        pyr = audio_energy_device(p2, out=(arena[o_16:o_16 + n_16], arena[o_512:o_512 + n_512]))
                 prepared.append((ssim, ft, pcm, pyr, sr))
             for sd in side:
                 main.wait_stream(sd)
