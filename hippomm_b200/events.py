@@ -164,7 +164,7 @@ class EventBank:
         return idx, score, mx[: self.nev]
 
     def _search_exact(self, query, k: int):
-        from .bank import _EPS_BF16, _T2ENUM, search_rows
+        from .bank import _EPS_BF16, _T2ENUM
 
         b = self.bank
         if b.src is None:
@@ -193,11 +193,28 @@ class EventBank:
         sizes = self._offsets_d[1:] - self._offsets_d[:-1]
         kth = score[:, k - 1]
         ok = (sizes <= kc) | ((idx[:, k - 1] >= 0) & (torch.isnan(kth) | (kth >= c_score[:, kc - 1] + eps)))
-        for j in torch.nonzero(~ok).reshape(-1).tolist():          # rare: straight from the event's own rows
-            o0, o1 = int(self.offsets[j]), int(self.offsets[j + 1])
-            ri, rs = search_rows(b.src[o0:o1], q, min(k, o1 - o0))
-            idx[j, : ri.numel()] = ri
-            score[j, : ri.numel()] = rs.to(torch.float32)
+        # the others: EVERY row of the event re-scored from the original rows, all such events in one launch pair
+        # (video-like events hold runs of near-duplicate frames, so this is not rare: a Python loop of per-event
+        # passes cost milliseconds per query on a store of 2,000 events)
+        bad = torch.nonzero(~ok).reshape(-1)
+        step = max(1, (1 << 24) // max(int(sizes.max().item()) if bad.numel() else 1, 1))      # <= 16M candidates a round
+        for c0 in range(0, bad.numel(), step):
+            sel = bad[c0:c0 + step]
+            sz = sizes[sel]
+            m = int(sz.max().item())
+            col = torch.arange(m, dtype=torch.int64, device=dev)[None, :]
+            cand = torch.where(col < sz[:, None], self._offsets_d[sel][:, None] + col, torch.full_like(col, -1)).contiguous()
+            keys = torch.empty((sel.numel(), m), dtype=torch.int64, device=dev)
+            i2 = torch.empty((sel.numel(), k), dtype=torch.int64, device=dev)
+            s2 = torch.empty((sel.numel(), k), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.hippo_rescore(b.src.data_ptr(), _T2ENUM[b.src.dtype], b.n, b.d, b.src.stride(0), 0,
+                                             q.data_ptr(), _lib.HIPPO_F32, 0, sel.numel(), cand.data_ptr(), m,
+                                             keys.data_ptr(), None, stream))
+                _lib.check(lib.hippo_topk_merge(keys.data_ptr(), 1, sel.numel(), m, k, i2.data_ptr(), s2.data_ptr(),
+                                                None, stream))
+            idx[sel] = torch.where(i2 >= 0, i2 - self._offsets_d[sel][:, None], i2)
+            score[sel] = s2
         valid = idx >= 0
         # np.max over the event's top-k as the reference takes it (hm:3156): NaN wins
         mx = torch.where(valid, score, torch.full_like(score, float("-inf"))).max(dim=1).values
