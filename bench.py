@@ -1296,7 +1296,8 @@ def run_next_rows(device, peaks):
         "cpu_port": {"ms_per_video_minute": t_pre_cpu * 1e3, "cores": os.cpu_count(), "kind": "port",
                      "gpu_result_identical": bool(list(holder["saved"][0]) == list(want_saved[0]))},
         "config": "extract_frames_from_video's save decisions (bp:179-228) on 1,800 decoded 224x224 frames resident in HBM: "
-                  "a sequential chain (every decision moves the anchor), one small launch + one readback per round of 8 candidates",
+                  "a sequential chain (every decision moves the anchor): ONE launch scores every (candidate, earlier candidate) pair up to "
+                  "24 candidates apart, the decision rule walks that table on the host",
     }
     log(f"[extra] key-frame pre-filter, 60 s at 30 fps: {t_pre * 1e3:.2f} ms (CPU port {t_pre_cpu * 1e3:.0f} ms, identical: "
         f"{list(holder['saved'][0]) == list(want_saved[0])})")

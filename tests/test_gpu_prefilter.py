@@ -32,8 +32,10 @@ def test_prefilter_matches_oracle_on_raw_frames(cuda_device, params, window):
 
     frames = cases.prefilter_frames()
     want = O.select_saved_frames(frames, **params)
-    got = select_saved_frames(frames, window=window, **params)
-    assert got[0] == want[0] and got[1] == want[1]
+    # band 0: fallback launches only; 2: the table misses whenever the anchor is more than two candidates back; 24: table
+    for band in (0, 2, 24):
+        got = select_saved_frames(frames, window=window, band=band, **params)
+        assert got[0] == want[0] and got[1] == want[1], band
 
 
 def test_prefilter_edge_cases(cuda_device):
@@ -55,4 +57,6 @@ def test_dedup_matches_oracle(cuda_device, threshold):
 
     for i, win in enumerate(cases.dedup_windows()):
         for window in (1, 4):
-            assert dedup_window_frames(win, threshold, window=window) == O.dedup_window_frames(win, threshold), (i, window)
+            for band in (0, 3, 128):
+                assert dedup_window_frames(win, threshold, window=window, band=band) == \
+                    O.dedup_window_frames(win, threshold), (i, window, band)
