@@ -196,12 +196,14 @@ class EventBank:
         # the others: EVERY row of the event re-scored from the original rows, all such events in one launch pair
         # (video-like events hold runs of near-duplicate frames, so this is not rare: a Python loop of per-event
         # passes cost milliseconds per query on a store of 2,000 events)
-        bad = torch.nonzero(~ok).reshape(-1)
-        step = max(1, (1 << 24) // max(int(sizes.max().item()) if bad.numel() else 1, 1))      # <= 16M candidates a round
-        for c0 in range(0, bad.numel(), step):
+        bad = torch.nonzero(~ok).reshape(-1)                       # the one host synchronisation of this path
+        sizes_h = np.diff(self.offsets)
+        bad_h = bad.cpu().numpy()
+        step = max(1, (1 << 24) // max(int(sizes_h[bad_h].max()) if len(bad_h) else 1, 1))     # <= 16M candidates a round
+        for c0 in range(0, len(bad_h), step):
             sel = bad[c0:c0 + step]
             sz = sizes[sel]
-            m = int(sz.max().item())
+            m = int(sizes_h[bad_h[c0:c0 + step]].max())
             col = torch.arange(m, dtype=torch.int64, device=dev)[None, :]
             cand = torch.where(col < sz[:, None], self._offsets_d[sel][:, None] + col, torch.full_like(col, -1)).contiguous()
             keys = torch.empty((sel.numel(), m), dtype=torch.int64, device=dev)
@@ -243,8 +245,15 @@ class EventBank:
                 idx.contiguous().data_ptr(), score.contiguous().data_ptr(), self.nev, k, self._toffsets_d.data_ptr(),
                 self._times_d.data_ptr(), _cuda.ptr(en), float(pad), top, ev.data_ptr(), oi.data_ptr(), sc.data_ptr(),
                 win.data_ptr(), cnt.data_ptr(), _cuda.stream_ptr()))
-        c = int(cnt.item())
-        return ev[:c].cpu().numpy(), oi[:c].cpu().numpy(), sc[:c].cpu().numpy(), win[:c].cpu().numpy()
+        # one readback: everything as fp64 columns (event and row numbers are far below 2^53)
+        packed = torch.cat([cnt.to(torch.float64), ev.to(torch.float64), oi.to(torch.float64), sc.to(torch.float64),
+                            win.reshape(-1)]).cpu().numpy()
+        c = int(packed[0])
+        ev_h = packed[1:1 + top][:c].astype(np.int32)
+        oi_h = packed[1 + top:1 + 2 * top][:c].astype(np.int64)
+        sc_h = packed[1 + 2 * top:1 + 3 * top][:c].astype(np.float32)
+        win_h = packed[1 + 3 * top:].reshape(top, 2)[:c].copy()
+        return ev_h, oi_h, sc_h, win_h
 
     # ------------------------------------------------------------ persistence ----
     def save(self, path: str) -> None:
