@@ -1257,11 +1257,49 @@ def run_next_rows(device, peaks):
     for q in qs[:4]:
         O.find_relevant_segments(q, sub, "vision")
     t_cpu = (time.perf_counter() - t0) / 4 * (n_events / len(sub))
+    # f-1: the binary bank file against the reference's store format (embeddings as decimal text in JSON, hm:110-133 /
+    # hm:334-335, reloaded to float64 lists -> arrays, hm:386-395)
+    import json as _json
+    import tempfile
+    persist = {}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "events.hippobank")
+            t0 = time.perf_counter()
+            eb.save(path)
+            t_save = time.perf_counter() - t0
+            size = os.path.getsize(path)
+            t0 = time.perf_counter()
+            eb2 = EventBank.load(path, device=device)
+            torch.cuda.synchronize()
+            t_load = time.perf_counter() - t0
+            ok_file = bool(torch.equal(eb2.bank.rows[: eb2.bank.n], eb.bank.rows[: eb.bank.n]) and
+                           np.array_equal(eb2.offsets, eb.offsets))
+            del eb2
+            jp = os.path.join(td, "event.json")
+            t0 = time.perf_counter()
+            for ev in events[:8]:
+                with open(jp, "w") as f:
+                    _json.dump({"features": {"vision": ev.features["vision"].tolist()}}, f)
+            t_jsave = (time.perf_counter() - t0) / 8 * n_events
+            t0 = time.perf_counter()
+            for _ in range(8):
+                with open(jp) as f:
+                    np.array(_json.load(f)["features"]["vision"], dtype=np.float64)
+            t_jload = (time.perf_counter() - t0) / 8 * n_events
+        persist = {"bank_file_bytes": size, "save_s": t_save, "load_to_device_s": t_load, "round_trip_identical": ok_file,
+                   "reference_json": {"save_s": t_jsave, "load_s": t_jload, "kind": "port",
+                                      "sample": f"json.dump / json.load + np.array(float64) of the vision features of 8 events, "
+                                                f"scaled x{n_events // 8}"}}
+        log(f"[extra] bank file of {n_events} events: save {t_save:.2f} s, load to the device {t_load:.2f} s "
+            f"({size / 1e9:.2f} GB, identical: {ok_file}); the reference's JSON: save {t_jsave:.0f} s, load {t_jload:.0f} s")
+    except Exception as e:
+        persist = {"error": repr(e)}
     bank_bytes = eb.bank.n * eb.bank.d_pad * 2 + eb.bank.n * 4
     out["recall_cross_event"] = {
         "ms_per_query_search": t_search * 1e3, "ms_per_query_recall": t_recall * 1e3,
         "events": n_events, "rows": int(eb.bank.n), "k_per_event": 5, "top": 5,
-        "bank_build_from_host_s": t_build,
+        "bank_build_from_host_s": t_build, "persistence": persist,
         "roofline": {"bound": "hbm", "achieved": bank_bytes / t_search / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": bank_bytes / t_search / 1e9 / peaks["hbm"],
                      "note": "ms_per_query_search: one segmented top-5 pass over the bf16 rows of every event "
