@@ -185,6 +185,65 @@ class MemoryBank:
             for st in stage:
                 st.record_stream(main)
 
+    def fill_from_parts(self, parts, chunk_rows: int = 1 << 15) -> None:
+        """Rows 0 .. n-1 from a LIST of host arrays laid end to end (the per-event feature arrays of a ThetaEvent store),
+        through the same two pinned + two device staging buffers as `_fill_pipelined`: runs of consecutive arrays are
+        gathered into one pinned chunk, so the many small arrays cost one DMA and one build launch per chunk."""
+        d = self.d
+        dt = self.src.dtype if self.src is not None else torch.float32
+        for p in parts:
+            if np.asarray(p).dtype == np.float64:
+                dt = torch.float64
+        npdt = np.float64 if dt == torch.float64 else np.float32
+        if sum(len(p) for p in parts) != self.n:
+            raise ValueError("the parts must add up to the bank's rows")
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            copy = _copy_stream(dev)
+            pin = _pinned_pair(chunk_rows * d, dt)
+            stage = [torch.empty((chunk_rows, d), dtype=dt, device=dev) for _ in range(2)]
+            h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+            built = [torch.cuda.Event(), torch.cuda.Event()]
+            copy.wait_stream(main)
+            # split the parts into pieces of at most chunk_rows rows, then group pieces into chunks
+            pieces = []
+            for p in parts:
+                a = np.asarray(p)
+                for r0 in range(0, len(a), chunk_rows):
+                    pieces.append(a[r0:r0 + chunk_rows])
+            i = c = 0
+            start = 0
+            while i < len(pieces):
+                b = c & 1
+                if c >= 2:
+                    h2d_done[b].synchronize()                # the DMA that last read this pinned buffer
+                view = pin[b][: chunk_rows * d].numpy().reshape(chunk_rows, d)
+                m = 0
+                while i < len(pieces) and m + len(pieces[i]) <= chunk_rows:
+                    k = len(pieces[i])
+                    if k:
+                        np.copyto(view[m:m + k], pieces[i], casting="same_kind" if pieces[i].dtype.kind == "f" else "unsafe")
+                    m += k
+                    i += 1
+                if m == 0:
+                    continue
+                src = pin[b][: m * d].view(m, d)
+                with torch.cuda.stream(copy):
+                    if c >= 2:
+                        copy.wait_event(built[b])            # the build kernel that last read this device buffer
+                    stage[b][:m].copy_(src, non_blocking=True)
+                    h2d_done[b].record(copy)
+                main.wait_event(h2d_done[b])
+                self.fill(start, stage[b][:m])
+                built[b].record(main)
+                start += m
+                c += 1
+            for st in stage:
+                st.record_stream(main)
+            for e in h2d_done:
+                e.synchronize()                              # the pinned pair is shared: done before anyone reuses it
+
     def fill(self, start: int, rows) -> None:
         """(Re)build rows [start, start + len(rows)) from a host array / tensor on any device."""
         lib = _lib.load()

@@ -104,9 +104,9 @@ class EventBank:
         wide = any(f.dtype == np.float64 for f in rows)
         bank = MemoryBank(int(offsets[-1]), d, device=device, keep_rows=keep_rows,
                           rows_dtype=torch.float64 if wide else torch.float32)
-        for f, o in zip(rows, offsets[:-1]):
-            if len(f):
-                bank.fill(int(o), f if f.dtype in (np.float32, np.float64) else f.astype(np.float32))
+        # events are small (hundreds of rows): runs of consecutive events share one pinned chunk, one DMA and one build
+        # launch (a fill per event is a 1 MB copy + a launch each, ~0.5 ms: a second for a store of 2,000 events)
+        bank.fill_from_parts([f if f.dtype in (np.float32, np.float64) else f.astype(np.float32) for f in rows])
         return cls(bank, offsets, toffsets, np.concatenate(times) if times else np.zeros(0), index, modality)
 
     # ----------------------------------------------------------------- search ----
