@@ -220,3 +220,45 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
     assert ref["cpu_baseline"]["value"] == ref["value"] == ref["e2e"]["value"]
+
+
+def test_frame_filter_speculation_is_decision_neutral(monkeypatch):
+    """The greedy frame filters with the device scorer replaced by the oracle's SSIM / MSE: whatever
+    the speculative table holds (no table, a band that keeps missing, all pairs) and however many candidates a fallback
+    round takes, the decisions equal the restated reference's -- the host logic (candidate gate, table indexing,
+    fallback) without a GPU."""
+    import cases
+    from hippomm_b200 import prefilter
+
+    def scorer(sub, a, b, range_mode=0, out=None):
+        fr = sub.numpy()
+        gray = [O.bgr2gray(f) if f.shape[-1] == 3 else f[..., 0] for f in fr]
+        ss, ms = [], []
+        for i, j in zip(a.tolist(), b.tolist()):
+            g1, g2 = gray[i].astype(np.float64), gray[j].astype(np.float64)
+            ms.append(float(np.mean((g1 / 255.0 - g2 / 255.0) ** 2)))
+            if min(g1.shape) < 7:
+                ss.append(float("nan"))
+            elif range_mode == 1:
+                with np.errstate(all="ignore"):
+                    ss.append(float(O.structural_similarity(g1 / 255.0, g2 / 255.0, data_range=1.0)))
+            else:
+                with np.errstate(all="ignore"):
+                    ss.append(float(O.structural_similarity(gray[i], gray[j], data_range=float(int(gray[i].max()) - int(gray[i].min())))))
+        return torch.tensor(ss, dtype=torch.float64), torch.tensor(ms, dtype=torch.float64)
+
+    monkeypatch.setattr(prefilter, "frame_pair_scores_device", scorer)
+    monkeypatch.setattr(prefilter, "_frames_to_device", lambda frames: torch.from_numpy(np.ascontiguousarray(frames)))
+    frames = cases.prefilter_frames()[:150, ::2, ::2]                   # 150 frames of 48 x 48: seconds on the host
+    for params in (dict(video_fps=30.0, max_diff_threshold=0.3, check_interval=10),
+                   dict(video_fps=60.0, max_diff_threshold=0.05, check_interval=7),       # the 1 s gate skips candidates
+                   dict(video_fps=10.0, max_diff_threshold=0.9, check_interval=1)):
+        want = O.select_saved_frames(frames, **params)
+        for band, window in ((0, 3), (1, 8), (2, 1), (24, 8)):
+            got = prefilter.select_saved_frames(frames, band=band, window=window, **params)
+            assert got[0] == want[0] and got[1] == want[1], (params, band, window)
+    for win in cases.dedup_windows()[:5]:
+        small = np.ascontiguousarray(win[:, ::3, ::3])
+        want = O.dedup_window_frames(small, 0.3)
+        for band, window in ((0, 1), (1, 4), (128, 4)):
+            assert prefilter.dedup_window_frames(small, 0.3, window=window, band=band) == want, (band, window)
