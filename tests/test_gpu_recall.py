@@ -239,3 +239,24 @@ def test_event_store_hook_wiring_and_llm_delegation(cuda_device):
     finally:
         store.uninstall_event_store(saved)
     assert QARecallSystem()._find_relevant_audio_segments(None) == ["from the reference"]
+
+
+def test_bank_from_many_small_arrays_equals_bank_from_one_array(cuda_device):
+    """`MemoryBank.fill_from_parts` (the per-event feature arrays of a store through shared pinned chunks): arrays smaller
+    and larger than a chunk, empty ones, fp32 and fp64 mixed -- the same bf16 rows, norms and kept originals as one
+    `from_rows` call on the concatenation."""
+    from hippomm_b200 import MemoryBank
+
+    rng = np.random.default_rng(5)
+    d = 192
+    sizes = [3, 0, 700, 1, 2500, 64, 0, 999, 5]
+    for dts in ([np.float32] * len(sizes), [np.float32, np.float64] * 4 + [np.float32]):
+        parts = [rng.standard_normal((n, d)).astype(dt) for n, dt in zip(sizes, dts)]
+        wide = any(dt == np.float64 for dt in dts)
+        whole = np.concatenate([p.astype(np.float64 if wide else np.float32) for p in parts])
+        ref = MemoryBank.from_rows(whole, keep_rows=True)
+        bank = MemoryBank(len(whole), d, keep_rows=True, rows_dtype=torch.float64 if wide else torch.float32)
+        bank.fill_from_parts(parts, chunk_rows=1024)
+        torch.cuda.synchronize()
+        assert torch.equal(bank.rows[: bank.n], ref.rows[: ref.n]) and torch.equal(bank.norm[: bank.n], ref.norm[: ref.n])
+        assert torch.equal(bank.src, ref.src)

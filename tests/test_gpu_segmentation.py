@@ -354,13 +354,15 @@ def test_overlapped_pipeline_equals_stage_by_stage(cuda_device, chunk_pairs):
     assert [tuple(x) for x in bv[: int(cv.item())].cpu().numpy().tolist()] == [tuple(w) for w in wv]
 
 
-@pytest.mark.parametrize("env", [{"HIPPO_FOLLOW_US": "1"}, {"HIPPO_FOLLOW_US": "30"}, {"HIPPO_PATTERN_FOLLOW": "0"}])
+@pytest.mark.parametrize("env", [{"HIPPO_FOLLOW_US": "1"}, {"HIPPO_FOLLOW_US": "30"}, {"HIPPO_PATTERN_FOLLOW": "0"},
+                                 {"HIPPO_PATTERN_L2PIN": "0"}])
 def test_follow_mode_chain_suspends_and_completes(cuda_device, env, monkeypatch):
     """The boundary chain that FOLLOWS the SSIM kernels pair by pair (segment.cu follow mode) gives up when a pair does
     not arrive within its limit -- a serialising profiler, a launch-blocking debug run -- and the final resumable pass
     finishes the stream: with a 1 us / 30 us limit most calls take that path at some segment, and the boundaries, the
     SSIM values and the count must still be those of the stage-by-stage calls.  HIPPO_PATTERN_FOLLOW=0 is the
-    chunk-by-chunk chain (also what streams longer than the staged 6,000 frames use)."""
+    chunk-by-chunk chain (also what streams longer than the staged 6,000 frames use); HIPPO_PATTERN_L2PIN=0 runs the
+    follower without the persisting-L2 window over the block sums."""
     from hippomm_b200 import synth
     from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device, pattern_separation_device,
                                            segment_boundaries_device)
@@ -404,3 +406,36 @@ def test_stream_longer_than_the_staged_frames(cuda_device):
     torch.cuda.synchronize()
     n = int(c0.item())
     assert n > 200 and int(c1.item()) == n and torch.equal(b0[:n], b1[:n]) and torch.equal(s1, ssim)
+
+
+def test_a_silent_span_does_not_wait_for_video_but_a_loud_one_does(cuda_device):
+    """Follow mode releases the video threads of a span as soon as a window of it is KNOWN to be silent (the audio boundary
+    overwrites the video boundary, hm:1061-1077) and waits for the pairs otherwise: audio that decides every span, audio
+    with no silence at all (every span is decided by the frames), and no audio -- each equal to the stage-by-stage
+    calls and to the oracle."""
+    from hippomm_b200 import synth
+    from hippomm_b200.segmentation import (audio_energy_device, frame_pair_scores_device, pattern_separation_device,
+                                           segment_boundaries_device)
+
+    nsec, sr = 600, 8000
+    frames, _ = synth.frame_stream(51, nsec, 64, 64, min_scene=4, max_scene=45)
+    fd = torch.from_numpy(frames).to(cuda_device)
+    ft = torch.arange(nsec, dtype=torch.float64, device=cuda_device)
+    ssim, _ = frame_pair_scores_device(fd, range_mode=0)
+    rng = np.random.default_rng(52)
+    loud = (rng.standard_normal(nsec * sr) * 3000).astype(np.int16)                    # -20 dBFS everywhere
+    often = loud.copy()
+    for t0 in range(7, nsec, 13):                                                      # a second of silence every 13 s
+        often[t0 * sr:(t0 + 1) * sr] = 0
+    for pcm in (often, loud, None):
+        pd = torch.from_numpy(pcm.reshape(-1, 1)).to(cuda_device) if pcm is not None else None
+        pyr = audio_energy_device(pd) if pd is not None else None
+        b0, c0 = segment_boundaries_device(ssim, ft, pd, pyr, sr, 30.0, 10.0, 0.95, -40.0, 256)
+        for _ in range(3):
+            b1, c1, s1 = pattern_separation_device(fd, ft, pd, sr, 30.0, 10.0, 0.95, -40.0, 256)
+            torch.cuda.synchronize()
+            n = int(c0.item())
+            assert n > 15 and int(c1.item()) == n and torch.equal(b0[:n], b1[:n]) and torch.equal(s1, ssim)
+        x = pcm.astype(np.float64).reshape(-1, 1) / 32768.0 if pcm is not None else None
+        want = O.segment_boundaries(O.adjacent_ssim(frames), [float(i) for i in range(nsec)], x, sr if pcm is not None else None)
+        assert [tuple(v) for v in b1[:n].cpu().numpy().tolist()] == [tuple(w) for w in want]
