@@ -155,6 +155,7 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   // left alone every such read goes to DRAM behind that traffic and a segment takes ~3 us instead of 1.4.  The pyramid
   // kernels (aux) and the chain (chain) therefore access the sums with the persisting L2 policy.
   const char* pin_env = getenv("HIPPO_PATTERN_L2PIN");      // 0 switches it off (A/B)
+  bool l2_window = false;
   if (follow && has_audio && !(pin_env && atoi(pin_env) == 0)) {
     static thread_local int l2_ready = 0;            // 0 = not tried, 1 = set-aside configured, -1 = unavailable
     if (l2_ready == 0) {
@@ -181,6 +182,7 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
       cudaStreamSetAttribute(aux, cudaStreamAttributeAccessPolicyWindow, &av);
       cudaStreamSetAttribute(chain, cudaStreamAttributeAccessPolicyWindow, &av);
       cudaGetLastError();
+      l2_window = true;
     }
   }
 
@@ -244,6 +246,13 @@ hippo_status hippo_pattern_separation(const uint8_t* frames, int32_t nf, int32_t
   mark(chain, "final pass end");
   HIPPO_CUDA(cudaEventRecord(e_done, chain));
   HIPPO_CUDA(cudaStreamWaitEvent(main, e_done, 0));
+  if (l2_window) {
+    // the window applied to the launches above; whatever the caller runs on these streams next is not ours to mark
+    cudaStreamAttrValue off{};
+    cudaStreamSetAttribute(aux, cudaStreamAttributeAccessPolicyWindow, &off);
+    cudaStreamSetAttribute(chain, cudaStreamAttributeAccessPolicyWindow, &off);
+    cudaGetLastError();
+  }
   if (dbg) {
     mark(main, "joined");
     cudaStreamSynchronize(main);

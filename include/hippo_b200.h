@@ -405,7 +405,8 @@ hippo_status hippo_segment_boundaries_resume(const hippo_stream_desc* streams, i
  * With audio the call sets aside up to 8 MB of L2 for persisting accesses (cudaLimitPersistingL2CacheSize, once per
  * host thread) and gives side_streams_host[1] and [2] an access-policy window over out_e512: the chain reads those sums
  * while the frame kernels stream ~0.9 GB through L2, and without the window every read goes to DRAM behind that
- * traffic (a segment then takes ~3 us instead of 1.4).  HIPPO_PATTERN_L2PIN=0 switches it off.
+ * traffic (a segment then takes ~3 us instead of 1.4); the window is taken off the two streams again before the call
+ * returns.  HIPPO_PATTERN_L2PIN=0 switches it off.
  * A segment whose span holds a window KNOWN to be silent is settled by the audio boundary (it overwrites the video
  * boundary, hm:1061-1077), so the chain does not wait for SSIM values of that span that are still pending.
  */
