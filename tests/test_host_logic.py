@@ -262,3 +262,43 @@ def test_frame_filter_speculation_is_decision_neutral(monkeypatch):
         want = O.dedup_window_frames(small, 0.3)
         for band, window in ((0, 1), (1, 4), (128, 4)):
             assert prefilter.dedup_window_frames(small, 0.3, window=window, band=band) == want, (band, window)
+
+
+def test_ssim_lane_mappings_cover_every_window_and_every_pixel_exactly_once():
+    """A host model of the ownership rules of csrc/frames.cu (ssim_item<4> / <7>, ssim_nchunks): for every width, each
+    window column belongs to exactly one (chunk, lane, k), each image column is counted for the squared error by exactly
+    one lane, and an owned window only needs columns that its own warp holds (two lanes to the right with 4 columns
+    per lane, one lane with 7)."""
+    def nchunks(out_cols, cpl):
+        if out_cols <= 0:
+            return 1
+        return max(1, (out_cols - 1 + 216) // 217 if cpl == 7 else (out_cols + 119) // 120)
+
+    for cpl, own_lanes in ((4, 30), (7, 31)):
+        for w in list(range(7, 260)) + [320, 433, 434, 440, 441, 442, 600, 651, 652, 1280, 1920]:
+            out_cols = w - 6
+            pitch = (w + 6) // 7 * 8 if cpl == 7 else (w + 3) & ~3
+            nch = nchunks(out_cols, cpl)
+            win_owner = np.zeros(out_cols, dtype=np.int32)
+            px_owner = np.zeros(w, dtype=np.int32)
+            for c in range(nch):
+                last = c == nch - 1
+                for lane in range(32):
+                    g = c * own_lanes + lane
+                    col_ok = g * (4 if cpl == 4 else 8) < pitch
+                    col0 = g * cpl
+                    if col_ok and (lane < own_lanes or last):
+                        px_owner[col0:min(col0 + cpl, w)] += 1            # the bytes beyond the row are zero padding
+                    for k in range(cpl):
+                        if cpl == 7:
+                            own = (lane < own_lanes or (k == 0 and last)) and col0 + k < out_cols
+                        else:
+                            own = lane < own_lanes and col0 + k < out_cols
+                        if own:
+                            win_owner[col0 + k] += 1
+                            last_col = col0 + k + 6                       # the window spans columns col0+k .. col0+k+6
+                            lane_of_last = last_col // cpl - c * own_lanes
+                            assert lane_of_last <= 31 and lane_of_last - lane <= (2 if cpl == 4 else 1), (cpl, w, c, lane, k)
+                            assert last_col < w
+            assert (win_owner == 1).all(), (cpl, w, np.nonzero(win_owner != 1)[0][:5])
+            assert (px_owner == 1).all(), (cpl, w, np.nonzero(px_owner != 1)[0][:5])
