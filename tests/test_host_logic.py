@@ -302,3 +302,30 @@ def test_ssim_lane_mappings_cover_every_window_and_every_pixel_exactly_once():
                             assert last_col < w
             assert (win_owner == 1).all(), (cpl, w, np.nonzero(win_owner != 1)[0][:5])
             assert (px_owner == 1).all(), (cpl, w, np.nonzero(px_owner != 1)[0][:5])
+
+
+def test_dp2a_permutes_of_the_ssim_row_step_give_the_window_moments():
+    """The SSIM row step (csrc/frames.cu) forms, per column, bn = byte_perm(wa, wb, sel) = (x, y, y, x) and
+    hn = byte_perm(bn, 0, 0x4140) = x | y << 16, then dp2a.lo(hn, bn) and dp2a.hi(hn, bn).  Emulated with PTX's
+    definitions for all byte pairs and all four byte positions: x^2 + y^2, 2xy and the packed sum x | y << 16."""
+    def byte_perm(x, y, sel):
+        src = [(x >> (8 * i)) & 0xff for i in range(4)] + [(y >> (8 * i)) & 0xff for i in range(4)]
+        return sum(src[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
+
+    def dp2a(a, b, c, hi):                     # a: two 16-bit halves, b: bytes 0,1 (lo) or 2,3 (hi), unsigned
+        a0, a1 = a & 0xffff, a >> 16
+        b0, b1 = (b >> (16 if hi else 0)) & 0xff, (b >> (24 if hi else 8)) & 0xff
+        return (c + a0 * b0 + a1 * b1) & 0xffffffff
+
+    rng = np.random.default_rng(3)
+    for k in range(4):
+        sel = k | ((4 + k) << 4) | ((4 + k) << 8) | (k << 12)
+        for x, y in [(0, 0), (255, 255), (255, 0), (0, 255), (1, 254)] + [tuple(int(v) for v in rng.integers(0, 256, 2)) for _ in range(200)]:
+            wa = int(rng.integers(0, 1 << 32)) & ~(0xff << (8 * k)) | (x << (8 * k))
+            wb = int(rng.integers(0, 1 << 32)) & ~(0xff << (8 * k)) | (y << (8 * k))
+            bn = byte_perm(wa, wb, sel)
+            hn = byte_perm(bn, 0, 0x4140)
+            assert bn == x | (y << 8) | (y << 16) | (x << 24)
+            assert hn == x | (y << 16)
+            assert dp2a(hn, bn, 7, hi=False) == 7 + x * x + y * y
+            assert dp2a(hn, bn, 7, hi=True) == 7 + 2 * x * y
